@@ -1,0 +1,173 @@
+"""numpy twin of the C oracle -- an independent restatement used to cross-check it.
+
+TEST INFRASTRUCTURE ONLY.  Vectorised over t; taps are visited in ascending order with
+a separate multiply and add per tap (numpy ufuncs never fuse), so results are
+bit-identical to the reference's Java loops.  Works on the
+sparse (a trous) form: zero taps of the dense upsampled filter add +-0.0 only.
+
+Cites: CORE/internal/ScalarOps.java:700-723,790-808,818-835,909-916;
+CORE/util/MathUtils.java:30-51; CORE/modwt/MODWTTransform.java:139-175,244-296,672-684;
+CORE/modwt/MultiLevelMODWTTransform.java:244-251,554-645,795-806;
+CORE/modwt/SymmetricAlignmentStrategy.java:43-117;
+CORE/modwt/MutableMultiLevelMODWTResult.java:97-118;
+CORE/swt/VectorWaveSwtAdapter.java:505-520,627-645.
+"""
+import math
+
+import numpy as np
+
+PERIODIC, ZERO_PADDING, SYMMETRIC = 0, 1, 2
+S = 1.0 / math.sqrt(2.0)
+
+
+def mirror(idx, n):
+    m = np.mod(idx, 2 * n)
+    return np.where(m < n, m, 2 * n - 1 - m)
+
+
+def _gather(x, idx, mode):
+    """x[ext(idx)] and a validity mask (False => term skipped, ZERO_PADDING only)."""
+    n = x.shape[-1]
+    if mode == PERIODIC:
+        return x[..., np.mod(idx, n)], None
+    if mode == SYMMETRIC:
+        return x[..., mirror(idx, n)], None
+    valid = (idx >= 0) & (idx < n)
+    return x[..., np.clip(idx, 0, n - 1)], valid
+
+
+def conv(x, f, mode, dilation=1):
+    """out[t] = sum_k x[ext(t - k*dilation)] * f[k]; x may be [..., N]."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[-1]
+    t = np.arange(n)
+    acc = np.zeros_like(x)
+    for k in range(len(f)):
+        xv, valid = _gather(x, t - k * dilation, mode)
+        term = xv * f[k]
+        acc = acc + term if valid is None else np.where(valid, acc + term, acc)
+    return acc
+
+
+def forward_single(x, h, g, mode):
+    hs, gs = np.asarray(h) * S, np.asarray(g) * S
+    return conv(x, hs, mode), conv(x, gs, mode)
+
+
+def inverse_single(v, w, hr, gr, mode, batch_variant=False):
+    v, w = np.asarray(v, dtype=np.float64), np.asarray(w, dtype=np.float64)
+    hs, gs = np.asarray(hr) * S, np.asarray(gr) * S
+    n = v.shape[-1]
+    t = np.arange(n)
+    acc = np.zeros_like(v)
+    for k in range(len(hs)):
+        if mode == SYMMETRIC and not batch_variant:
+            idx = t - k
+        else:
+            idx = t + k
+        vv, valid = _gather(v, idx, mode)
+        wv, _ = _gather(w, idx, mode)
+        term = hs[k] * vv + gs[k] * wv
+        acc = acc + term if valid is None else np.where(valid, acc + term, acc)
+    return acc
+
+
+def decompose(x, h, g, levels, mode):
+    hs, gs = np.asarray(h) * S, np.asarray(g) * S
+    cur = np.asarray(x, dtype=np.float64)
+    ws = []
+    for level in range(1, levels + 1):
+        d = 1 << (level - 1)
+        if (len(hs) - 1) * d + 1 > cur.shape[-1]:
+            raise ValueError("VAL_TOO_LARGE")
+        ws.append(conv(cur, gs, mode, d))
+        cur = conv(cur, hs, mode, d)
+    return np.stack(ws, axis=0), cur
+
+
+def alignment(wavelet_id, l0, level):
+    detail_plus = True
+    if l0 <= 2:
+        return True, (0 if level <= 1 else -1), True, 0
+    approx_plus = False
+    if wavelet_id == 1:
+        dh, dg = (0 if level <= 1 else -1), (1 if level >= 3 else 0)
+    elif wavelet_id == 2:
+        dh, dg = (0 if level <= 1 else 1), (1 if level >= 2 else 0)
+    elif wavelet_id == 3:
+        approx_plus, detail_plus, dh, dg = True, False, 0, 0
+    elif wavelet_id == 4:
+        dh, dg = (0, 0) if level <= 1 else ((1, 0) if level == 2 else (1, 1))
+    elif wavelet_id == 5:
+        approx_plus, detail_plus, dh, dg = True, False, (0 if level <= 1 else 1), 0
+    elif wavelet_id == 6:
+        detail_plus = False
+        dh, dg = (0, 0) if level <= 1 else (-1, 1)
+    elif l0 >= 12:
+        if level <= 1:
+            dh, dg = 0, 0
+        else:
+            dh = dg = 0 if level % 2 == 0 else -1
+    else:
+        dh, dg = (0, 0) if level <= 1 else (-1, 0)
+    return approx_plus, dh, detail_plus, dg
+
+
+def tau_j(l0, level):
+    return ((l0 - 1) * (1 << (level - 1))) // 2
+
+
+def synth_level(a, dcoef, hr, gr, level, mode, wavelet_id=0):
+    a, dcoef = np.asarray(a, dtype=np.float64), np.asarray(dcoef, dtype=np.float64)
+    hs, gs = np.asarray(hr) * S, np.asarray(gr) * S
+    n = a.shape[-1]
+    d = 1 << (level - 1)
+    t = np.arange(n)
+    acc = np.zeros_like(a)
+    if mode == PERIODIC:
+        for k in range(len(hs)):
+            acc = acc + hs[k] * a[..., np.mod(t + k * d, n)]
+        for k in range(len(gs)):
+            acc = acc + gs[k] * dcoef[..., np.mod(t + k * d, n)]
+    elif mode == ZERO_PADDING:
+        for k in range(len(hs)):
+            idx = t + k * d
+            valid = idx < n
+            idc = np.clip(idx, 0, n - 1)
+            acc = np.where(valid, acc + (hs[k] * a[..., idc] + gs[k] * dcoef[..., idc]), acc)
+    else:
+        ap, dh, dp, dg = alignment(wavelet_id, len(hs), level)
+        th, tg = tau_j(len(hs), level) + dh, tau_j(len(gs), level) + dg
+        for k in range(len(hs)):
+            idx = t + k * d - th if ap else t - k * d + th
+            acc = acc + hs[k] * a[..., mirror(idx, n)]
+        for k in range(len(gs)):
+            idx = t + k * d - tg if dp else t - k * d + tg
+            acc = acc + gs[k] * dcoef[..., mirror(idx, n)]
+    return acc
+
+
+def reconstruct(w, v, hr, gr, mode, wavelet_id=0, detail_mask=None, use_approx=True):
+    levels = w.shape[0]
+    if detail_mask is None:
+        detail_mask = (1 << levels) - 1
+    cur = np.array(v, dtype=np.float64) if use_approx else np.zeros_like(v)
+    for level in range(levels, 0, -1):
+        dj = w[level - 1] if (detail_mask >> (level - 1)) & 1 else np.zeros_like(v)
+        cur = synth_level(cur, dj, hr, gr, level, mode, wavelet_id)
+    return cur
+
+
+def threshold(c, thr, soft):
+    c = np.asarray(c, dtype=np.float64)
+    a = np.abs(c)
+    if soft:
+        return np.where(a > thr, np.sign(c) * (a - thr), 0.0)
+    return np.where(a <= thr, 0.0, c)
+
+
+def universal_threshold(w1):
+    a = np.sort(np.abs(np.asarray(w1, dtype=np.float64)))
+    n = a.size
+    med = (a[n // 2 - 1] + a[n // 2]) / 2.0 if n % 2 == 0 else a[n // 2]
+    return (med / 0.6745) * math.sqrt(2 * math.log(n))
