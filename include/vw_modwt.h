@@ -1,0 +1,213 @@
+/*
+ * vw_modwt.h -- C ABI of the B200-native MODWT / SWT engine (libvwmodwt.so).
+ *
+ * This is the drop-in boundary for VectorWave's MODWT/SWT hot path.  The reference
+ * (MorphIQ-Labs/VectorWave) is pure Java with no FFI; the entry points below are what a
+ * Panama FFM (java.lang.foreign) binding of that path calls -- INTEGRATION.md shows the
+ * downcall stubs.  Each function cites the reference interface it replaces
+ * (CORE = vectorwave-core/src/main/java/com/morphiqlabs/wavelet,
+ *  EXT  = vectorwave-extensions/src/main/java/com/morphiqlabs/wavelet).
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no exceptions cross the ABI.  Every call returns a
+ *    vw_status; vw_last_error(ctx) gives the message for the last failure on that ctx.
+ *  - All data are IEEE fp64.  Signals are row-major [batch][n] with a row stride `ld`
+ *    (in elements).  Multi-level details are [levels][batch][n]: level j (1-based,
+ *    1 = finest, CORE/modwt/MultiLevelMODWTResult.java:32-99) starts at
+ *    w + (j-1)*level_stride, signal b at + b*ld.
+ *  - Filters cross the ABI ALREADY SCALED by 1/sqrt(2) (hs[k] = h[k]*(1.0/Math.sqrt(2.0)),
+ *    one rounding, CORE/internal/ScalarOps.java:909-916, CORE/modwt/MODWTTransform.java:139-150)
+ *    and NOT upsampled: the engine applies the a-trous spacing 2^(j-1) itself.  Wavelet
+ *    tables, the level-cap policy and the SYMMETRIC alignment table stay on the host side
+ *    so the reference's quirks stay the reference's.
+ *  - Data pointers are HOST pointers unless VW_FLAG_DEVICE_PTRS is set.  Host buffers are
+ *    staged through ctx-owned device memory (pinned host memory from vw_alloc_pinned makes
+ *    the copies asynchronous DMA).  There is no CPU compute path: without a CUDA device
+ *    vw_init fails with VW_ECUDA and nothing else can be called.
+ *  - A ctx is bound to one device and one stream; use one ctx per host thread.
+ */
+#ifndef VW_MODWT_H
+#define VW_MODWT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VW_API __attribute__((visibility("default")))
+#else
+#define VW_API
+#endif
+
+#define VW_ABI_VERSION 1
+#define VW_MAX_FILTER_TAPS 128 /* coif17 = 102 taps is the reference's longest table */
+#define VW_MAX_LEVELS 32
+
+/* Status codes; names follow CORE/exception/ErrorCode.java:24-118. */
+typedef enum vw_status {
+    VW_OK = 0,
+    VW_ENULL = 1,        /* VAL_NULL_ARGUMENT   -> NullPointerException */
+    VW_ENONFINITE = 3,   /* VAL_NON_FINITE_VALUES -> InvalidSignalException (ValidationUtils.validateFiniteValues) */
+    VW_ETOOLARGE = 5,    /* VAL_TOO_LARGE: (L-1)*2^(j-1)+1 > n, CORE/modwt/MultiLevelMODWTTransform.java:717-729 */
+    VW_EEMPTY = 6,       /* VAL_EMPTY           -> InvalidSignalException */
+    VW_ELENGTH = 7,      /* VAL_LENGTH_MISMATCH -> IllegalArgumentException (shape errors, EXT/extensions/modwt/BatchMODWT.java:201-212) */
+    VW_EBOUNDARY = 103,  /* CFG_UNSUPPORTED_BOUNDARY_MODE, CORE/modwt/MODWTTransform.java:96-110 */
+    VW_ELEVEL = 104,     /* CFG_INVALID_DECOMPOSITION_LEVEL, CORE/modwt/MultiLevelMODWTTransform.java:226-239 */
+    VW_ESTATE = 301,     /* STATE_CLOSED / STATE_INVALID */
+    VW_EINVAL = 400,     /* other IllegalArgumentException */
+    VW_ENOMEM = 500,     /* device or pinned allocation failed */
+    VW_ECUDA = 501,      /* CUDA runtime error; message in vw_last_error */
+    VW_EUNSUPPORTED = 502
+} vw_status;
+
+/* CORE/api/BoundaryMode.java:26-50.  CONSTANT is rejected exactly as the reference does. */
+typedef enum vw_boundary {
+    VW_PERIODIC = 0,
+    VW_ZERO_PADDING = 1,
+    VW_SYMMETRIC = 2,
+    VW_CONSTANT = 3 /* always VW_EBOUNDARY */
+} vw_boundary;
+
+/* Summation order of one synthesis stage. */
+typedef enum vw_synth_order {
+    VW_ORDER_SPLIT = 0, /* all H taps, then all G taps: CORE/modwt/MultiLevelMODWTTransform.java:578-589,602-642 */
+    VW_ORDER_PAIR = 1   /* sum += h*V + g*W per tap: CORE/modwt/MODWTTransform.java:246-295, MultiLevel ZERO :591-601 */
+} vw_synth_order;
+
+enum {
+    VW_FLAG_DEVICE_PTRS = 1u << 0,  /* data pointers are device pointers on ctx's device */
+    VW_FLAG_CHECK_FINITE = 1u << 1, /* reject NaN/Inf inputs (VW_ENONFINITE) like the Java API does */
+    VW_FLAG_BITEXACT = 1u << 2,     /* separate multiply/add roundings in Java's tap order (no FMA);
+                                       runs the per-level kernels; results are bit-identical to the JVM */
+    VW_FLAG_NO_FUSE = 1u << 3,      /* force the per-level kernels (diagnostics) */
+    VW_FLAG_NO_SYNC = 1u << 4       /* device-pointer calls only: return after enqueueing on the ctx stream */
+};
+
+/* Per-level alignment of one synthesis stage, generalising every inverse the reference has:
+ *   out[t] = sum_k hs[k]*V[ext(t + sigma_h*(k*d - tau_h))] (+) gs[k]*W[ext(t + sigma_g*(k*d - tau_g))]
+ * d = 2^(level-1).  PERIODIC / ZERO_PADDING and single-level batch SYMMETRIC: {+1,0,+1,0}
+ * (t+l; CORE/modwt/MODWTTransform.java:246-272,672-684); single-level SYMMETRIC: {-1,0,-1,0}
+ * (t-l; :277-295); multi-level SYMMETRIC: from SymmetricAlignmentStrategy.decide + computeTauJ
+ * (CORE/modwt/SymmetricAlignmentStrategy.java:43-117, MultiLevelMODWTTransform.java:602-642,795-806). */
+typedef struct vw_align {
+    int32_t sigma_h; /* +1 "plus" orientation, -1 "minus" */
+    int32_t tau_h;
+    int32_t sigma_g;
+    int32_t tau_g;
+} vw_align;
+
+typedef struct vw_ctx vw_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+/* device < 0 selects the current CUDA device.  Fails with VW_ECUDA when no device exists. */
+VW_API int vw_init(int device, vw_ctx **out);
+VW_API int vw_destroy(vw_ctx *ctx);
+VW_API const char *vw_last_error(const vw_ctx *ctx);
+VW_API const char *vw_status_name(int status);
+VW_API int vw_abi_version(void);
+/* Run on an existing cudaStream_t (e.g. the caller's framework stream); NULL = ctx-owned stream. */
+VW_API int vw_set_stream(vw_ctx *ctx, void *cuda_stream);
+VW_API int vw_synchronize(vw_ctx *ctx);
+VW_API int vw_device_index(const vw_ctx *ctx);
+/* Tuning knobs: "tile" (samples per CTA tile), "fuse" (max levels per launch), "threads". 0 = auto. */
+VW_API int vw_set_option(vw_ctx *ctx, const char *name, int64_t value);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+VW_API int64_t vw_launch_count(const vw_ctx *ctx);
+
+/* ---- memory (Java: MemorySegment.reinterpret over these) ---------------------------- */
+VW_API void *vw_alloc_pinned(size_t bytes);
+VW_API void vw_free_pinned(void *p);
+VW_API int vw_device_alloc(vw_ctx *ctx, size_t bytes, void **out);
+VW_API int vw_device_free(vw_ctx *ctx, void *p);
+VW_API int vw_copy_h2d(vw_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+VW_API int vw_copy_d2h(vw_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+
+/* ---- level admissibility ---------------------------------------------------------- */
+/* CORE/modwt/MultiLevelMODWTTransform.java:455-501 calculateMaxLevels: 0 if n <= l, else the
+ * largest j with (l-1)*2^(j-1)+1 <= n, found by `while (j < cap)` then `return j-1` -- so
+ * cap = 10 (MAX_DECOMPOSITION_LEVELS) yields at most 9.  cap <= 0: no cap. */
+VW_API int vw_max_levels(int64_t n, int32_t l, int32_t cap);
+
+/* ---- primitives ------------------------------------------------------------------- */
+/* WaveletOperations.{circular,zeroPadding,symmetric}ConvolveMODWT (CORE/WaveletOperations.java:29,48,59;
+ * kernels CORE/internal/ScalarOps.java:700-723,790-808,818-835):
+ *   out[t] = sum_{l<lf} x[ext(t-l)] * filter[l]   with an arbitrary dense (pre-scaled) filter. */
+VW_API int vw_conv_modwt(vw_ctx *ctx, const double *x, int64_t n, const double *filter, int64_t lf, int32_t mode,
+                  double *out, uint32_t flags);
+
+/* ---- analysis --------------------------------------------------------------------- */
+/* MODWTTransform.forward / forwardBatch (levels = 1; CORE/modwt/MODWTTransform.java:131,486),
+ * MultiLevelMODWTTransform.decompose (CORE/modwt/MultiLevelMODWTTransform.java:209-255),
+ * VectorWaveSwtAdapter.forward (CORE/swt/VectorWaveSwtAdapter.java:198-204),
+ * BatchMODWT.singleLevelAoS / multiLevelAoS (EXT/extensions/modwt/BatchMODWT.java:62,90):
+ *   V_0 = x;  W_j[t] = sum_k gs[k]*V_{j-1}[ext(t - k*2^(j-1))];  V_j likewise with hs.
+ * Requires (l-1)*2^(levels-1)+1 <= n when levels > 1 (VW_ETOOLARGE); levels == 1 accepts any
+ * n >= 1 (true multi-wrap, CORE/internal/ScalarOps.java:711-717).  The level CAP is host policy.
+ * w: [levels][batch][n] with strides (level_stride_w, ldw); vj: [batch][n] stride ldv. */
+VW_API int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const double *hs,
+                     const double *gs, int32_t l, int32_t levels, int32_t mode, double *w, int64_t ldw,
+                     int64_t level_stride_w, double *vj, int64_t ldv, uint32_t flags);
+
+/* ---- synthesis -------------------------------------------------------------------- */
+/* MODWTTransform.inverse / inverseBatch (CORE/modwt/MODWTTransform.java:203,531),
+ * MultiLevelMODWTTransform.reconstruct / reconstructFromLevel / reconstructLevels (:339,361,398),
+ * VectorWaveSwtAdapter.inverse (CORE/swt/VectorWaveSwtAdapter.java:435-474),
+ * BatchMODWT.inverseSingleLevelAoS / inverseMultiLevelAoS (EXT/extensions/modwt/BatchMODWT.java:122,151).
+ * align: levels entries (index j-1) or NULL for {+1,0,+1,0} at every level.
+ * detail_mask bit (j-1) clear => W_j is treated as zeros (partial reconstruction);
+ * use_approx == 0 => V_J is treated as zeros. */
+VW_API int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_stride_w, const double *vj,
+                     int64_t ldv, int64_t batch, int64_t n, const double *hs, const double *gs, int32_t l,
+                     int32_t levels, int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask,
+                     int32_t use_approx, double *xout, int64_t ldx, uint32_t flags);
+
+/* ---- thresholding / SWT denoise ------------------------------------------------------- */
+/* MutableMultiLevelMODWTResult.applyThreshold (CORE/modwt/MutableMultiLevelMODWTResult.java:83-118):
+ * in place over `batch` rows of n; soft: |c|>t ? sign(c)*(|c|-t) : 0; hard: |c|<=t ? 0 : c.
+ * thresholds is a HOST array (1 value, or `batch` values when per_row != 0) regardless of flags. */
+VW_API int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t ld, const double *thresholds,
+                 int32_t per_row, int32_t soft, uint32_t flags);
+
+/* VectorWaveSwtAdapter.applyUniversalThreshold's threshold (CORE/swt/VectorWaveSwtAdapter.java:505-520,627-645):
+ * per row: median(|w1|)/0.6745*sqrt(2 ln n), median of an even count = mean of the two middle
+ * order statistics (exact selection, no sort).  thresholds_out: `batch` doubles on the HOST. */
+VW_API int vw_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld,
+                           double *thresholds_out, uint32_t flags);
+
+/* VectorWaveSwtAdapter.denoise (CORE/swt/VectorWaveSwtAdapter.java:532-562): decompose, threshold every
+ * detail level (threshold < 0 => universal, per signal), reconstruct.  thresholds_out may be NULL. */
+VW_API int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const double *hs,
+                   const double *gs, int32_t l, int32_t levels, int32_t mode, const vw_align *align, int32_t order,
+                   double threshold, int32_t soft, double *out, int64_t ldo, double *thresholds_out, uint32_t flags);
+
+/* sum of squares per row: MultiLevelMODWTResult.getDetailEnergyAtLevel / getApproximationEnergy
+ * (CORE/modwt/MultiLevelMODWTResultImpl.java:91-139).  out: `batch` doubles on the HOST. */
+VW_API int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags);
+
+/* ---- span-sharded long signals (one rank's part; halos already exchanged) ------------------ */
+/* A rank owns samples [s, s+n_local) of one long signal.  For a group of `nlevels` levels starting
+ * at `first_level`, analysis needs the halo = (l-1)*2^(first_level-1)*(2^nlevels-1) samples of
+ * V_{first_level-1} that precede the span (from the left neighbour; the last rank for PERIODIC wrap).
+ * vin points at the start of [halo | span] (halo+n_local contiguous samples, device memory).
+ * Writes W_j[span] for the group's levels and V_{first_level+nlevels-1}[span].  No boundary rule is
+ * applied: the halo IS the boundary (the host fills it per BoundaryMode).  Reference precedent for the
+ * halo semantics: EXT/extensions/modwt/BatchSIMDMODWT.java:447-507 (left history of L_j-1 samples). */
+VW_API int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t n_local, const double *hs,
+                          const double *gs, int32_t l, int32_t first_level, int32_t nlevels, double *w,
+                          int64_t level_stride_w, double *vout, uint32_t flags);
+/* Synthesis of the same group: vin and each W_j are [span | halo] with the RIGHT halo
+ * (first samples of the right neighbour), halo >= (l-1)*2^(first_level-1)*(2^nlevels-1); w rows are
+ * level_stride_w apart, each halo+n_local long.  Writes V_{first_level-1}[span].  PERIODIC/ZERO index rule (t+k*d). */
+VW_API int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64_t level_stride_w, int64_t halo,
+                          int64_t n_local, const double *hs, const double *gs, int32_t l, int32_t first_level,
+                          int32_t nlevels, int32_t order, double *vout, uint32_t flags);
+/* halo length the two calls above require */
+VW_API int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VW_MODWT_H */

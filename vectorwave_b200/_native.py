@@ -1,0 +1,399 @@
+"""ctypes binding of libvwmodwt.so (include/vw_modwt.h) -- the same C ABI the Java FFM binding uses.
+
+There is no CPU compute path: if the shared library is missing or no CUDA device is present,
+`Engine.get()` raises NativeEngineError.  Host numpy arrays are staged by the shim; torch CUDA
+tensors are passed as device pointers (zero copy) and the work is enqueued on torch's current stream.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentException, InvalidSignalException,
+                     NativeEngineError, NullPointerException)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvwmodwt.so")
+
+FLAG_DEVICE_PTRS = 1 << 0
+FLAG_CHECK_FINITE = 1 << 1
+FLAG_BITEXACT = 1 << 2
+FLAG_NO_FUSE = 1 << 3
+FLAG_NO_SYNC = 1 << 4
+
+ORDER_SPLIT, ORDER_PAIR = 0, 1
+
+VW_OK = 0
+_STATUS = {
+    1: (NullPointerException, None),
+    3: (InvalidSignalException, ErrorCode.VAL_NON_FINITE_VALUES),
+    5: (InvalidArgumentException, ErrorCode.VAL_TOO_LARGE),
+    6: (InvalidSignalException, ErrorCode.VAL_EMPTY),
+    7: (IllegalArgumentException, None),
+    103: (InvalidArgumentException, ErrorCode.CFG_UNSUPPORTED_BOUNDARY_MODE),
+    104: (InvalidArgumentException, ErrorCode.CFG_INVALID_DECOMPOSITION_LEVEL),
+    400: (IllegalArgumentException, None),
+}
+
+
+class VwAlign(C.Structure):
+    _fields_ = [("sigma_h", C.c_int32), ("tau_h", C.c_int32), ("sigma_g", C.c_int32), ("tau_g", C.c_int32)]
+
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_u32 = C.c_uint32
+
+# name -> (restype, argtypes); also the list tests check against include/vw_modwt.h
+SIGNATURES = {
+    "vw_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "vw_destroy": (C.c_int, [_vp]),
+    "vw_last_error": (C.c_char_p, [_vp]),
+    "vw_status_name": (C.c_char_p, [C.c_int]),
+    "vw_abi_version": (C.c_int, []),
+    "vw_set_stream": (C.c_int, [_vp, _vp]),
+    "vw_synchronize": (C.c_int, [_vp]),
+    "vw_device_index": (C.c_int, [_vp]),
+    "vw_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "vw_launch_count": (_i64, [_vp]),
+    "vw_alloc_pinned": (_vp, [C.c_size_t]),
+    "vw_free_pinned": (None, [_vp]),
+    "vw_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "vw_device_free": (C.c_int, [_vp, _vp]),
+    "vw_copy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "vw_copy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "vw_max_levels": (C.c_int, [_i64, _i32, _i32]),
+    "vw_conv_modwt": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _u32]),
+    "vw_modwt_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _i64, _vp,
+                                   _i64, _u32]),
+    "vw_modwt_inverse": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32,
+                                   C.POINTER(VwAlign), _i32, C.c_uint64, _i32, _vp, _i64, _u32]),
+    "vw_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _i32, _i32, _u32]),
+    "vw_universal_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
+    "vw_swt_denoise": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, C.POINTER(VwAlign), _i32,
+                                 C.c_double, _i32, _vp, _i64, _dp, _u32]),
+    "vw_energy": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
+    "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
+    "vw_modwt_inverse_span": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _i32, _vp, _u32]),
+    "vw_span_halo": (_i64, [_i32, _i32, _i32]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libvwmodwt.so and declare every entry point.  Works without a GPU (symbol checks)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeEngineError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback for the MODWT engine)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _np_rows(a, what="signal"):
+    """host array -> (2-D float64 view with contiguous rows, was_1d)."""
+    if a is None:
+        raise NullPointerException(f"{what} cannot be null")
+    a = np.asarray(a, dtype=np.float64)
+    one_d = a.ndim == 1
+    if one_d:
+        a = a.reshape(1, -1)
+    if a.ndim != 2:
+        raise IllegalArgumentException(f"{what} must be 1-D or 2-D, got {a.ndim}-D")
+    if a.shape[1] > 1 and a.strides[1] != 8 or (a.shape[0] > 1 and a.strides[0] % 8) or \
+            (a.shape[0] > 1 and a.strides[0] < a.shape[1] * 8):
+        a = np.ascontiguousarray(a)
+    return a, one_d
+
+
+def _ld(a):
+    if _is_torch(a):
+        return a.stride(0) if a.shape[0] > 1 else max(a.shape[1], 1)
+    return a.strides[0] // 8 if a.shape[0] > 1 else max(a.shape[1], 1)
+
+
+def _ptr(a):
+    return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+
+def _fp(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One native context (device + stream + scratch) per CUDA device, shared per process."""
+    _engines = {}
+    _lock = threading.Lock()
+
+    def __init__(self, device):
+        self.lib = load_library()
+        ctx = _vp()
+        rc = self.lib.vw_init(int(device), C.byref(ctx))
+        if rc != VW_OK:
+            raise NativeEngineError(
+                f"vw_init(device={device}) failed with {self.lib.vw_status_name(rc).decode()}: the MODWT engine "
+                "needs a CUDA device (no CPU fallback exists)")
+        self.ctx = ctx
+        self.device = self.lib.vw_device_index(ctx)
+        self._call_lock = threading.Lock()
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            try:
+                import torch
+                device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            except Exception:
+                device = 0
+        with cls._lock:
+            eng = cls._engines.get(device)
+            if eng is None:
+                eng = cls._engines[device] = Engine(device)
+        return eng
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == VW_OK:
+            return
+        msg = self.lib.vw_last_error(self.ctx).decode(errors="replace")
+        name = self.lib.vw_status_name(rc).decode()
+        exc, code = _STATUS.get(rc, (NativeEngineError, None))
+        if code is not None:
+            raise exc(f"[{code.value}] {msg}", code)
+        raise exc(f"{name}: {msg}")
+
+    def _bind_stream(self, *arrays):
+        """device pointers => run on torch's current stream; returns the flag word."""
+        if any(_is_torch(a) for a in arrays if a is not None):
+            import torch
+            for a in arrays:
+                if a is None:
+                    continue
+                if not _is_torch(a) or not a.is_cuda or a.dtype != torch.float64:
+                    raise IllegalArgumentException("device calls need float64 CUDA tensors for every buffer")
+                if a.device.index != self.device:
+                    raise IllegalArgumentException(f"tensor on cuda:{a.device.index}, engine on cuda:{self.device}")
+            self._check(self.lib.vw_set_stream(self.ctx, _vp(torch.cuda.current_stream(self.device).cuda_stream)))
+            return FLAG_DEVICE_PTRS | FLAG_NO_SYNC
+        self._check(self.lib.vw_set_stream(self.ctx, None))
+        return 0
+
+    def set_option(self, name, value):
+        self._check(self.lib.vw_set_option(self.ctx, name.encode(), int(value)))
+
+    def launch_count(self):
+        return int(self.lib.vw_launch_count(self.ctx))
+
+    def synchronize(self):
+        self._check(self.lib.vw_synchronize(self.ctx))
+
+    def max_levels(self, n, l, cap=10):
+        return int(self.lib.vw_max_levels(int(n), int(l), int(cap)))
+
+    @staticmethod
+    def _rows(x, what="signal"):
+        if x is None:
+            raise NullPointerException(f"{what} cannot be null")
+        if _is_torch(x):
+            one_d = x.dim() == 1
+            x2 = x.reshape(1, -1) if one_d else x
+            if x2.dim() != 2:
+                raise IllegalArgumentException(f"{what} must be 1-D or 2-D")
+            if x2.shape[1] > 1 and x2.stride(1) != 1:
+                x2 = x2.contiguous()
+            return x2, one_d
+        return _np_rows(x, what)
+
+    @staticmethod
+    def _empty_like_rows(x, *shape):
+        if _is_torch(x):
+            import torch
+            return torch.empty(shape, dtype=torch.float64, device=x.device)
+        return np.empty(shape, dtype=np.float64)
+
+    @staticmethod
+    def _align_array(align, levels):
+        if align is None:
+            return None
+        if len(align) != levels:
+            raise IllegalArgumentException("alignment table must have one entry per level")
+        arr = (VwAlign * levels)()
+        for j, (sh, th, sg, tg) in enumerate(align):
+            arr[j] = VwAlign(int(sh), int(th), int(sg), int(tg))
+        return arr
+
+    # -- primitives --------------------------------------------------------------------------
+    def conv(self, x, filt, mode, out=None, flags=0):
+        x2, _ = self._rows(x)
+        if x2.shape[0] != 1:
+            raise IllegalArgumentException("conv takes one signal")
+        filt = _fp(filt)
+        if _is_torch(x2):
+            import torch
+            fdev = torch.as_tensor(filt, device=x2.device)
+            res = out if out is not None else torch.empty_like(x2[0])
+            fl = self._bind_stream(x2, res) | flags
+            with self._call_lock:
+                self._check(self.lib.vw_conv_modwt(self.ctx, _vp(x2.data_ptr()), x2.shape[1], _vp(fdev.data_ptr()),
+                                                   filt.size, mode, _vp(res.data_ptr()), fl))
+            return res
+        res = out if out is not None else np.empty(x2.shape[1])
+        if res.dtype != np.float64 or not res.flags.c_contiguous or res.size != x2.shape[1]:
+            raise IllegalArgumentException("output must be a contiguous float64 array of the signal's length")
+        fl = self._bind_stream() | flags
+        with self._call_lock:
+            self._check(self.lib.vw_conv_modwt(self.ctx, _vp(x2.ctypes.data), x2.shape[1], _vp(filt.ctypes.data),
+                                               filt.size, mode, _vp(res.ctypes.data), fl))
+        return res
+
+    def forward(self, x, hs, gs, levels, mode, flags=0, w_out=None, v_out=None):
+        """x [B][N] (or [N]) -> (W [J][B][N], V_J [B][N]); same residency (numpy / torch.cuda) as x."""
+        x2, one_d = self._rows(x)
+        b, n = x2.shape
+        hs, gs = _fp(hs), _fp(gs)
+        if hs.size != gs.size:
+            raise IllegalArgumentException("low-pass and high-pass filters must have the same length")
+        lev = max(int(levels), 0)
+        w = w_out if w_out is not None else self._empty_like_rows(x2, max(lev, 1), b, max(n, 1))
+        v = v_out if v_out is not None else self._empty_like_rows(x2, b, max(n, 1))
+        fl = self._bind_stream(x2, w, v) | flags
+        ldw = w.stride(1) if _is_torch(w) else w.strides[1] // 8
+        lsw = w.stride(0) if _is_torch(w) else w.strides[0] // 8
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_forward(
+                self.ctx, _vp(_ptr(x2)), b, n, _ld(x2), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
+                int(levels), int(mode), _vp(_ptr(w)), ldw, lsw, _vp(_ptr(v)), _ld(v), fl))
+        if one_d:
+            return w[:, 0, :], v[0]
+        return w, v
+
+    def inverse(self, w, v, hs, gs, mode, align=None, order=ORDER_SPLIT, detail_mask=None, use_approx=True,
+                flags=0, out=None):
+        """W [J][B][N] (or [J][N]), V [B][N] (or [N]) -> x [B][N] (or [N])."""
+        if w is None or v is None:
+            raise NullPointerException("coefficients cannot be null")
+        one_d = (v.dim() if _is_torch(v) else np.ndim(v)) == 1
+        if not _is_torch(w):
+            w = np.asarray(w, dtype=np.float64)
+            v = np.asarray(v, dtype=np.float64)
+        if one_d:
+            w = w.reshape(w.shape[0], 1, -1)
+            v = v.reshape(1, -1)
+        if _is_torch(w):
+            w, v = w.contiguous(), v.contiguous()
+        else:
+            w, v = np.ascontiguousarray(w), np.ascontiguousarray(v)
+        levels, b, n = w.shape
+        if tuple(v.shape) != (b, n):
+            raise IllegalArgumentException("approximation and detail shapes must match")
+        hs, gs = _fp(hs), _fp(gs)
+        if detail_mask is None:
+            detail_mask = (1 << levels) - 1
+        res = out if out is not None else self._empty_like_rows(v, b, n)
+        fl = self._bind_stream(w, v, res) | flags
+        al = self._align_array(align, levels)
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_inverse(
+                self.ctx, _vp(_ptr(w)), n, b * n, _vp(_ptr(v)), n, b, n, hs.ctypes.data_as(_dp),
+                gs.ctypes.data_as(_dp), hs.size, levels, int(mode), al, int(order), C.c_uint64(detail_mask),
+                int(bool(use_approx)), _vp(_ptr(res)), _ld(res), fl))
+        return res[0] if one_d else res
+
+    def threshold(self, coeffs, thresholds, soft, flags=0):
+        """In place on `coeffs` ([B][N] or [N]); thresholds: scalar or per-row host values."""
+        c2, _ = self._rows(coeffs, "coefficients")
+        thr = np.atleast_1d(np.asarray(thresholds, dtype=np.float64))
+        per_row = int(thr.size > 1)
+        if per_row and thr.size != c2.shape[0]:
+            raise IllegalArgumentException("one threshold per row expected")
+        if not _is_torch(c2) and not np.shares_memory(c2, coeffs):
+            raise IllegalArgumentException("in-place thresholding needs a contiguous float64 array")
+        fl = self._bind_stream(c2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_threshold(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
+                                              thr.ctypes.data_as(_dp), per_row, int(bool(soft)), fl))
+        return coeffs
+
+    def universal_threshold(self, w1, flags=0):
+        w2, one_d = self._rows(w1, "coefficients")
+        out = np.empty(w2.shape[0])
+        fl = self._bind_stream(w2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_universal_threshold(self.ctx, _vp(_ptr(w2)), w2.shape[0], w2.shape[1], _ld(w2),
+                                                        out.ctypes.data_as(_dp), fl))
+        return float(out[0]) if one_d else out
+
+    def denoise(self, x, hs, gs, levels, mode, align=None, order=ORDER_SPLIT, threshold=-1.0, soft=True, flags=0):
+        x2, one_d = self._rows(x)
+        b, n = x2.shape
+        hs, gs = _fp(hs), _fp(gs)
+        res = self._empty_like_rows(x2, b, max(n, 1))
+        thr = np.empty(max(b, 1))
+        fl = self._bind_stream(x2, res) | flags
+        al = self._align_array(align, int(levels)) if align is not None else None
+        with self._call_lock:
+            self._check(self.lib.vw_swt_denoise(
+                self.ctx, _vp(_ptr(x2)), b, n, _ld(x2), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
+                int(levels), int(mode), al, int(order), float(threshold), int(bool(soft)), _vp(_ptr(res)), _ld(res),
+                thr.ctypes.data_as(_dp), fl))
+        return (res[0], float(thr[0])) if one_d else (res, thr)
+
+    def energy(self, c, flags=0):
+        c2, one_d = self._rows(c, "coefficients")
+        out = np.empty(c2.shape[0])
+        fl = self._bind_stream(c2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_energy(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
+                                           out.ctypes.data_as(_dp), fl))
+        return float(out[0]) if one_d else out
+
+    # -- span-sharded pieces (device tensors only) -----------------------------------------------
+    def span_halo(self, l, first_level, nlevels):
+        return int(self.lib.vw_span_halo(int(l), int(first_level), int(nlevels)))
+
+    def forward_span(self, vin_ext, halo, hs, gs, first_level, nlevels, flags=0):
+        """vin_ext: 1-D CUDA tensor [halo | span] -> (W [nlevels][n_local], V [n_local])."""
+        import torch
+        n_local = vin_ext.numel() - halo
+        hs, gs = _fp(hs), _fp(gs)
+        w = torch.empty((nlevels, max(n_local, 1)), dtype=torch.float64, device=vin_ext.device)
+        v = torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
+        fl = self._bind_stream(vin_ext, w, v) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_forward_span(
+                self.ctx, _vp(vin_ext.data_ptr()), int(halo), int(n_local), hs.ctypes.data_as(_dp),
+                gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), _vp(w.data_ptr()), w.stride(0),
+                _vp(v.data_ptr()), fl))
+        return w, v
+
+    def inverse_span(self, vin_ext, w_ext, halo, hs, gs, first_level, nlevels, order=ORDER_SPLIT, flags=0):
+        """vin_ext [span | halo], w_ext [nlevels][span | halo] (CUDA) -> V_{first-1} [n_local]."""
+        import torch
+        n_local = vin_ext.numel() - halo
+        hs, gs = _fp(hs), _fp(gs)
+        w_ext = w_ext.contiguous()
+        out = torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
+        fl = self._bind_stream(vin_ext, w_ext, out) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_inverse_span(
+                self.ctx, _vp(vin_ext.data_ptr()), _vp(w_ext.data_ptr()), w_ext.stride(0), int(halo), int(n_local),
+                hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), int(order),
+                _vp(out.data_ptr()), fl))
+        return out

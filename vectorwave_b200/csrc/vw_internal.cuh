@@ -1,0 +1,87 @@
+// vw_internal.cuh -- shared declarations of the MODWT engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "vw_modwt.h"
+
+#define VW_MODE_LINEAR 4  // internal: span calls -- indices outside the provided buffer are skipped
+
+// Pre-scaled base filters passed by value in kernel parameter space (constant bank).
+struct VwFilt {
+    double h[VW_MAX_FILTER_TAPS];
+    double g[VW_MAX_FILTER_TAPS];
+};
+
+// Compact filter block of the fused kernels (L <= 32): fully unrolled tap loops read these
+// straight from the constant bank as DFMA operands.
+#define VW_FUSED_MAX_L 32
+struct VwFilt32 {
+    double h[VW_FUSED_MAX_L];
+    double g[VW_FUSED_MAX_L];
+};
+
+struct vw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // grow-only device scratch (ping-pong V buffers, staged host I/O, selection workspaces)
+    static const int kScratch = 6;
+    void *scratch[kScratch] = {};
+    size_t scratch_bytes[kScratch] = {};
+    void *pinned = nullptr;  // small pinned mailbox for D2H scalars
+    size_t pinned_bytes = 0;
+    int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
+};
+
+int vw_fail(vw_ctx *ctx, int status, const char *fmt, ...);
+int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what);
+int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out);
+
+// ---- generic per-level kernels (vw_generic.cu): any n, l, dilation, mode ------------------
+int vw_launch_analysis_level(vw_ctx *ctx, const double *in, int64_t ld_in, double *v_out, int64_t ld_v,
+                             double *w_out, int64_t ld_w, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch,
+                             const VwFilt &f, int l, int64_t d, int mode, bool exact);
+int vw_launch_synthesis_level(vw_ctx *ctx, const double *v, int64_t ld_v, const double *w, int64_t ld_w, double *out,
+                              int64_t ld_o, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f,
+                              int l, int64_t d, int mode, vw_align al, bool pair, bool exact);
+int vw_launch_conv_dense(vw_ctx *ctx, const double *x, int64_t n, const double *filter, int64_t lf, int mode,
+                         double *out, bool exact);
+int vw_launch_threshold(vw_ctx *ctx, double *c, int64_t batch, int64_t n, int64_t ld, const double *thr_dev,
+                        int per_row, int soft);
+int vw_launch_nonfinite_count(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ld,
+                              unsigned long long *count_dev);
+int vw_launch_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out_dev);
+
+// ---- fused multi-level tile kernels (vw_fused.cu) ------------------------------------------
+// Return VW_OK when the fused path ran, VW_EUNSUPPORTED when the shape is not eligible (caller
+// falls back to the per-level kernels), anything else is an error.
+struct VwFusedFwd {
+    const double *x; int64_t ldx;            // V_{first-1}: [batch][n_in]
+    double *w; int64_t ldw, lsw;             // W_j rows for j = first .. first+nlev-1
+    double *v; int64_t ldv;                  // V_{first+nlev-1}
+    int64_t batch, n_in, t0, n_out;          // outputs cover input positions [t0, t0+n_out)
+    int l, first_level, nlevels, mode;
+};
+int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f);
+struct VwFusedInv {
+    const double *v; int64_t ldv;            // V_top: [batch][n_in]  (nullptr => zeros)
+    const double *w; int64_t ldw, lsw;       // W_j rows, j = first .. first+nlev-1
+    uint64_t detail_mask;                    // bit (j-first) clear => zeros
+    double *out; int64_t ldo;                // V_{first-1}
+    int64_t batch, n_in, n_out;              // outputs cover positions [0, n_out) of the input buffers
+    int l, first_level, nlevels, mode;
+    const double *thr_dev; int thr_per_row; int thr_soft;  // optional fused thresholding of W on load
+};
+int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f);
+
+// ---- exact order statistics (vw_select.cu) ---------------------------------------------------
+// median(|w1|) per row -> universal thresholds written to thr_dev[batch] (device).
+int vw_launch_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld,
+                                  double *thr_dev);

@@ -1,0 +1,766 @@
+// vw_shim.cu -- the C ABI of include/vw_modwt.h: argument validation with the reference's error
+// vocabulary, host<->device staging, and the level schedule (which levels fuse into which launch).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "vw_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+int vw_fail(vw_ctx *ctx, int status, const char *fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return VW_OK;
+    return vw_fail(ctx, e == cudaErrorMemoryAllocation ? VW_ENOMEM : VW_ECUDA, "CUDA error in %s: %s (%s)", what,
+                   cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->scratch[slot]);
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        int rc = vw_cuda_check(ctx, cudaMalloc(&ctx->scratch[slot], want), "scratch cudaMalloc");
+        if (rc) return rc;
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return VW_OK;
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int pinned_mailbox(vw_ctx *ctx, size_t bytes, void **out) {
+    if (ctx->pinned_bytes < bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        int rc = vw_cuda_check(ctx, cudaMallocHost(&ctx->pinned, want), "pinned mailbox");
+        if (rc) return rc;
+        ctx->pinned_bytes = want;
+    }
+    *out = ctx->pinned;
+    return VW_OK;
+}
+
+int load_filters(vw_ctx *ctx, const double *hs, const double *gs, int l, VwFilt &f) {
+    if (!hs || !gs) return vw_fail(ctx, VW_ENULL, "filter pointer is null");
+    if (l < 1 || l > VW_MAX_FILTER_TAPS)
+        return vw_fail(ctx, VW_EINVAL, "filter length %d outside [1, %d]", l, VW_MAX_FILTER_TAPS);
+    memset(&f, 0, sizeof f);
+    memcpy(f.h, hs, sizeof(double) * l);
+    memcpy(f.g, gs, sizeof(double) * l);
+    return VW_OK;
+}
+
+int check_mode(vw_ctx *ctx, int mode) {
+    if (mode == VW_PERIODIC || mode == VW_ZERO_PADDING || mode == VW_SYMMETRIC) return VW_OK;
+    return vw_fail(ctx, VW_EBOUNDARY, "MODWT only supports PERIODIC, ZERO_PADDING, and SYMMETRIC boundary modes (got %d)",
+                   mode);
+}
+
+// (l-1)*2^(levels-1)+1 <= n  (CORE/modwt/MultiLevelMODWTTransform.java:717-729); single level takes any n >= 1
+int check_levels(vw_ctx *ctx, int64_t n, int l, int levels) {
+    if (levels < 1 || levels > VW_MAX_LEVELS)
+        return vw_fail(ctx, VW_ELEVEL, "Invalid number of decomposition levels: %d", levels);
+    if (levels > 1) {
+        long double lj = (long double)(l - 1) * (long double)((int64_t)1 << (levels - 1)) + 1;
+        if (lj > (long double)n)
+            return vw_fail(ctx, VW_ETOOLARGE,
+                           "Upsampled filter length %.0Lf at level %d exceeds signal length %lld", lj, levels,
+                           (long long)n);
+    }
+    return VW_OK;
+}
+
+int check_finite(vw_ctx *ctx, const double *x_dev, int64_t batch, int64_t n, int64_t ld, const char *what) {
+    void *cnt = nullptr, *mb = nullptr;
+    int rc = vw_scratch(ctx, 5, 64, &cnt);
+    if (rc) return rc;
+    if ((rc = pinned_mailbox(ctx, 64, &mb))) return rc;
+    cudaMemsetAsync(cnt, 0, 8, ctx->stream);
+    if ((rc = vw_launch_nonfinite_count(ctx, x_dev, batch, n, ld, (unsigned long long *)cnt))) return rc;
+    cudaMemcpyAsync(mb, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "finite check"))) return rc;
+    unsigned long long bad = *(unsigned long long *)mb;
+    if (bad) return vw_fail(ctx, VW_ENONFINITE, "%s contains %llu non-finite value(s) (NaN or Infinity)", what, bad);
+    return VW_OK;
+}
+
+// 2-D strided copies between host rows and packed device rows
+int copy_rows(vw_ctx *ctx, void *dst, int64_t ld_dst, const void *src, int64_t ld_src, int64_t n, int64_t rows,
+              cudaMemcpyKind kind) {
+    if (n <= 0 || rows <= 0) return VW_OK;
+    return vw_cuda_check(ctx,
+                         cudaMemcpy2DAsync(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)n * 8,
+                                           (size_t)rows, kind, ctx->stream),
+                         "strided copy");
+}
+
+int finish(vw_ctx *ctx, uint32_t flags, bool host_io) {
+    if (host_io || !(flags & VW_FLAG_NO_SYNC)) return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+    return VW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident cores.  All pointers are device pointers here.
+// ------------------------------------------------------------------------------------------------
+
+// How many levels (>= 1) starting at `first` may share one fused launch, given the smem budget.
+int fuse_depth(const vw_ctx *ctx, int l, int first, int remaining, int64_t n) {
+    int cap = ctx->opt_fuse > 0 ? (int)ctx->opt_fuse : 4;
+    int f = std::min(cap, remaining);
+    // keep the fused halo (l-1)*2^(first-1)*(2^f-1) well below both the tile and the signal
+    while (f > 1) {
+        long double halo = (long double)(l - 1) * (long double)((int64_t)1 << (first - 1)) * (long double)(((int64_t)1 << f) - 1);
+        if (halo <= 2048.0L && halo <= (long double)n) break;
+        f--;
+    }
+    return f;
+}
+
+int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const VwFilt &f, int l,
+                   int levels, int mode, double *w, int64_t ldw, int64_t lsw, double *vj, int64_t ldv, uint32_t flags) {
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE);
+    // ping-pong approximations in scratch; the last level writes straight to vj
+    double *buf[2] = {nullptr, nullptr};
+    const double *cur = x;
+    int64_t ld_cur = ldx;
+    int level = 1, pp = 0;
+    while (level <= levels) {
+        int rc;
+        int nf = allow_fused ? fuse_depth(ctx, l, level, levels - level + 1, n) : 1;
+        bool last = level + nf - 1 == levels;
+        double *vout = vj;
+        int64_t ld_vout = ldv;
+        if (!last) {
+            if (!buf[pp]) {
+                void *p;
+                if ((rc = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p))) return rc;
+                buf[pp] = (double *)p;
+            }
+            vout = buf[pp];
+            ld_vout = n;
+        }
+        rc = VW_EUNSUPPORTED;
+        if (allow_fused) {
+            VwFusedFwd p{cur, ld_cur, w + (int64_t)(level - 1) * lsw, ldw, lsw, vout, ld_vout, batch, n, 0, n,
+                         l, level, nf, mode};
+            rc = vw_fused_forward(ctx, p, f);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+        }
+        if (rc == VW_EUNSUPPORTED) {
+            nf = 1;
+            last = level == levels;
+            if (last) { vout = vj; ld_vout = ldv; }
+            rc = vw_launch_analysis_level(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n, 0, n,
+                                          batch, f, l, (int64_t)1 << (level - 1), mode, exact);
+            if (rc) return rc;
+        }
+        cur = vout;
+        ld_cur = ld_vout;
+        pp ^= 1;
+        level += nf;
+    }
+    return VW_OK;
+}
+
+vw_align default_align() { return vw_align{1, 0, 1, 0}; }
+
+int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const double *vj, int64_t ldv,
+                   int64_t batch, int64_t n, const VwFilt &f, int l, int levels, int mode, const vw_align *align,
+                   int order, uint64_t detail_mask, int use_approx, double *xout, int64_t ldx, uint32_t flags,
+                   const double *thr_dev, int thr_per_row, int thr_soft) {
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    // the fused synthesis kernels implement the {+1,0,+1,0} index rule (t + k*d) -- PERIODIC and ZERO_PADDING
+    bool plain = true;
+    if (align)
+        for (int j = 0; j < levels; j++)
+            plain = plain && align[j].sigma_h == 1 && align[j].sigma_g == 1 && align[j].tau_h == 0 && align[j].tau_g == 0;
+    const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE) && plain && mode != VW_SYMMETRIC;
+    double *buf[2] = {nullptr, nullptr};
+    const double *cur = use_approx ? vj : nullptr;
+    int64_t ld_cur = ldv;
+    int level = levels, pp = 0;
+    while (level >= 1) {
+        int rc;
+        // group = levels [first, level], descending
+        int nf = 1;
+        if (allow_fused) {
+            int cap = ctx->opt_fuse > 0 ? (int)ctx->opt_fuse : 4;
+            nf = std::min(cap, level);
+            while (nf > 1) {
+                int first = level - nf + 1;
+                long double halo = (long double)(l - 1) * (long double)((int64_t)1 << (first - 1)) * (long double)(((int64_t)1 << nf) - 1);
+                if (halo <= 2048.0L && halo <= (long double)n) break;
+                nf--;
+            }
+        }
+        int first = level - nf + 1;
+        bool last = first == 1;
+        double *out = xout;
+        int64_t ld_out = ldx;
+        if (!last) {
+            if (!buf[pp]) {
+                void *p;
+                if ((rc = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p))) return rc;
+                buf[pp] = (double *)p;
+            }
+            out = buf[pp];
+            ld_out = n;
+        }
+        rc = VW_EUNSUPPORTED;
+        if (allow_fused) {
+            VwFusedInv p{cur, ld_cur, w + (int64_t)(first - 1) * lsw, ldw, lsw,
+                         (detail_mask >> (first - 1)) & ((nf >= 64 ? ~0ull : ((1ull << nf) - 1))),
+                         out, ld_out, batch, n, n, l, first, nf, mode, thr_dev, thr_per_row, thr_soft};
+            rc = vw_fused_inverse(ctx, p, f);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+        }
+        if (rc == VW_EUNSUPPORTED) {
+            nf = 1;
+            first = level;
+            last = first == 1;
+            if (last) { out = xout; ld_out = ldx; }
+            vw_align al = align ? align[level - 1] : default_align();
+            const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
+            if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
+            rc = vw_launch_synthesis_level(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
+                                           (int64_t)1 << (level - 1), mode, al, order == VW_ORDER_PAIR, exact);
+            if (rc) return rc;
+        }
+        cur = out;
+        ld_cur = ld_out;
+        pp ^= 1;
+        level -= nf;
+    }
+    return VW_OK;
+}
+
+int check_signal_args(vw_ctx *ctx, const void *x, int64_t batch, int64_t n, int64_t ld) {
+    if (!x) return vw_fail(ctx, VW_ENULL, "signal cannot be null");
+    if (batch < 1) return vw_fail(ctx, VW_ELENGTH, "signals must be non-null and non-empty (batch=%lld)", (long long)batch);
+    if (n < 1) return vw_fail(ctx, VW_EEMPTY, "Signal cannot be empty");
+    if (ld < n) return vw_fail(ctx, VW_ELENGTH, "row stride %lld shorter than signal length %lld", (long long)ld, (long long)n);
+    return VW_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int vw_abi_version(void) { return VW_ABI_VERSION; }
+
+const char *vw_status_name(int s) {
+    switch (s) {
+        case VW_OK: return "OK";
+        case VW_ENULL: return "VAL_NULL_ARGUMENT";
+        case VW_ENONFINITE: return "VAL_NON_FINITE_VALUES";
+        case VW_ETOOLARGE: return "VAL_TOO_LARGE";
+        case VW_EEMPTY: return "VAL_EMPTY";
+        case VW_ELENGTH: return "VAL_LENGTH_MISMATCH";
+        case VW_EBOUNDARY: return "CFG_UNSUPPORTED_BOUNDARY_MODE";
+        case VW_ELEVEL: return "CFG_INVALID_DECOMPOSITION_LEVEL";
+        case VW_ESTATE: return "STATE_INVALID";
+        case VW_EINVAL: return "ILLEGAL_ARGUMENT";
+        case VW_ENOMEM: return "OUT_OF_MEMORY";
+        case VW_ECUDA: return "CUDA_ERROR";
+        case VW_EUNSUPPORTED: return "UNSUPPORTED";
+        default: return "UNKNOWN";
+    }
+}
+
+int vw_init(int device, vw_ctx **out) {
+    if (!out) return VW_ENULL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return VW_ECUDA;  // no CPU path exists: fail loudly
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return VW_ECUDA; }
+    if (device >= count) return VW_EINVAL;
+    DeviceGuard g(device);
+    vw_ctx *ctx = new vw_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return VW_ECUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VW_ECUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return VW_OK;
+}
+
+int vw_destroy(vw_ctx *ctx) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return VW_OK;
+}
+
+const char *vw_last_error(const vw_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vw_set_stream(vw_ctx *ctx, void *s) {
+    if (!ctx) return VW_ENULL;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return VW_OK;
+}
+
+int vw_synchronize(vw_ctx *ctx) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+}
+
+int vw_device_index(const vw_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return VW_ENULL;
+    if (!strcmp(name, "tile")) ctx->opt_tile = value;
+    else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;
+    else if (!strcmp(name, "threads")) ctx->opt_threads = value;
+    else if (!strcmp(name, "poly")) ctx->opt_poly = value;
+    else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
+    return VW_OK;
+}
+
+int64_t vw_launch_count(const vw_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+void *vw_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    return p;
+}
+void vw_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+int vw_device_alloc(vw_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    return vw_cuda_check(ctx, cudaMalloc(out, bytes ? bytes : 16), "vw_device_alloc");
+}
+int vw_device_free(vw_ctx *ctx, void *p) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    return vw_cuda_check(ctx, cudaFree(p), "vw_device_free");
+}
+int vw_copy_h2d(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx || !dst || !src) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "h2d");
+    return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "h2d sync");
+}
+int vw_copy_d2h(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx || !dst || !src) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "d2h");
+    return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "d2h sync");
+}
+
+int vw_max_levels(int64_t n, int32_t l, int32_t cap) {
+    if (n <= l) return 0;
+    int limit = cap > 0 ? cap : 62;
+    int max_level = 1;
+    while (max_level < limit) {
+        long double lj = (long double)(l - 1) * (long double)((int64_t)1 << (max_level - 1)) + 1;
+        if (lj > (long double)n) break;
+        max_level++;
+    }
+    return max_level - 1;
+}
+
+int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels) {
+    if (l < 1 || first_level < 1 || nlevels < 1 || first_level + nlevels > 62) return -1;
+    return (int64_t)(l - 1) * ((int64_t)1 << (first_level - 1)) * (((int64_t)1 << nlevels) - 1);
+}
+
+int vw_conv_modwt(vw_ctx *ctx, const double *x, int64_t n, const double *filter, int64_t lf, int32_t mode, double *out,
+                  uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    if (!x || !filter || !out) return vw_fail(ctx, VW_ENULL, "signal, filter and output cannot be null");
+    int rc;
+    if ((rc = check_mode(ctx, mode))) return rc;
+    if (n < 1) return vw_fail(ctx, VW_EEMPTY, "Signal cannot be empty");
+    if (lf < 1) return vw_fail(ctx, VW_EEMPTY, "Filter cannot be empty");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    const double *xd = x, *fd = filter;
+    double *od = out;
+    if (!dev) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)(2 * n + lf) * 8, &p))) return rc;
+        double *base = (double *)p;
+        cudaMemcpyAsync(base, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(base + 2 * n, filter, (size_t)lf * 8, cudaMemcpyHostToDevice, ctx->stream);
+        xd = base; od = base + n; fd = base + 2 * n;
+    }
+    if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, 1, n, n, "signal"))) return rc;
+    if ((rc = vw_launch_conv_dense(ctx, xd, n, fd, lf, mode, od, flags & VW_FLAG_BITEXACT))) return rc;
+    if (!dev) cudaMemcpyAsync(out, od, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    return finish(ctx, flags, !dev);
+}
+
+int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const double *hs,
+                     const double *gs, int32_t l, int32_t levels, int32_t mode, double *w, int64_t ldw,
+                     int64_t level_stride_w, double *vj, int64_t ldv, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_mode(ctx, mode))) return rc;
+    if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
+    if (!w || !vj) return vw_fail(ctx, VW_ENULL, "output buffers cannot be null");
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    if ((rc = check_levels(ctx, n, l, levels))) return rc;
+    if (ldw < n || ldv < n || (levels > 1 && level_stride_w < (batch - 1) * ldw + n))
+        return vw_fail(ctx, VW_ELENGTH, "output strides too small for [levels][batch][n]");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    if (dev) {
+        if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, x, batch, n, ldx, "signal"))) return rc;
+        if ((rc = forward_device(ctx, x, batch, n, ldx, f, l, levels, mode, w, ldw, level_stride_w, vj, ldv, flags))) return rc;
+        return finish(ctx, flags, false);
+    }
+    // host buffers: stage x -> device (packed rows), run, stage W and V_J back
+    void *px, *pw;
+    size_t bn = (size_t)batch * (size_t)n;
+    if ((rc = vw_scratch(ctx, 2, bn * 8, &px))) return rc;
+    if ((rc = vw_scratch(ctx, 3, bn * 8 * (size_t)(levels + 1), &pw))) return rc;
+    double *xd = (double *)px, *wd = (double *)pw, *vd = wd + bn * (size_t)levels;
+    if ((rc = copy_rows(ctx, xd, n, x, ldx, n, batch, cudaMemcpyHostToDevice))) return rc;
+    if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, batch, n, n, "signal"))) return rc;
+    if ((rc = forward_device(ctx, xd, batch, n, n, f, l, levels, mode, wd, n, (int64_t)bn, vd, n, flags))) return rc;
+    for (int j = 0; j < levels; j++)
+        if ((rc = copy_rows(ctx, w + (int64_t)j * level_stride_w, ldw, wd + (size_t)j * bn, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
+    if ((rc = copy_rows(ctx, vj, ldv, vd, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
+    return finish(ctx, flags, true);
+}
+
+int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_stride_w, const double *vj, int64_t ldv,
+                     int64_t batch, int64_t n, const double *hs, const double *gs, int32_t l, int32_t levels,
+                     int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask, int32_t use_approx,
+                     double *xout, int64_t ldx, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_mode(ctx, mode))) return rc;
+    if (!w || !vj) return vw_fail(ctx, VW_ENULL, "coefficient buffers cannot be null");
+    if ((rc = check_signal_args(ctx, xout, batch, n, ldx))) return rc;
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    if ((rc = check_levels(ctx, n, l, levels))) return rc;
+    if (order != VW_ORDER_SPLIT && order != VW_ORDER_PAIR) return vw_fail(ctx, VW_EINVAL, "unknown synthesis order %d", order);
+    if (align)
+        for (int j = 0; j < levels; j++) {
+            const vw_align &a = align[j];
+            if ((a.sigma_h != 1 && a.sigma_h != -1) || (a.sigma_g != 1 && a.sigma_g != -1))
+                return vw_fail(ctx, VW_EINVAL, "alignment sigma must be +1 or -1 (level %d)", j + 1);
+            if (order == VW_ORDER_PAIR && (a.sigma_h != a.sigma_g || a.tau_h != a.tau_g))
+                return vw_fail(ctx, VW_EINVAL, "pair-added synthesis needs identical H and G alignment (level %d)", j + 1);
+        }
+    if (ldw < n || ldv < n) return vw_fail(ctx, VW_ELENGTH, "coefficient strides shorter than the signal length");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    if (dev) {
+        if (flags & VW_FLAG_CHECK_FINITE) {
+            if ((rc = check_finite(ctx, vj, batch, n, ldv, "approximation coefficients"))) return rc;
+            for (int j = 0; j < levels; j++)
+                if ((rc = check_finite(ctx, w + (int64_t)j * level_stride_w, batch, n, ldw, "detail coefficients"))) return rc;
+        }
+        if ((rc = inverse_device(ctx, w, ldw, level_stride_w, vj, ldv, batch, n, f, l, levels, mode, align, order,
+                                 detail_mask, use_approx, xout, ldx, flags, nullptr, 0, 0))) return rc;
+        return finish(ctx, flags, false);
+    }
+    void *px, *pw;
+    size_t bn = (size_t)batch * (size_t)n;
+    if ((rc = vw_scratch(ctx, 2, bn * 8, &px))) return rc;
+    if ((rc = vw_scratch(ctx, 3, bn * 8 * (size_t)(levels + 1), &pw))) return rc;
+    double *xd = (double *)px, *wd = (double *)pw, *vd = wd + bn * (size_t)levels;
+    for (int j = 0; j < levels; j++)
+        if ((rc = copy_rows(ctx, wd + (size_t)j * bn, n, w + (int64_t)j * level_stride_w, ldw, n, batch, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(ctx, vd, n, vj, ldv, n, batch, cudaMemcpyHostToDevice))) return rc;
+    if (flags & VW_FLAG_CHECK_FINITE)
+        if ((rc = check_finite(ctx, wd, (int64_t)(levels + 1) * batch, n, n, "coefficients"))) return rc;
+    if ((rc = inverse_device(ctx, wd, n, (int64_t)bn, vd, n, batch, n, f, l, levels, mode, align, order, detail_mask,
+                             use_approx, xd, n, flags, nullptr, 0, 0))) return rc;
+    if ((rc = copy_rows(ctx, xout, ldx, xd, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
+    return finish(ctx, flags, true);
+}
+
+int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t ld, const double *thresholds,
+                 int32_t per_row, int32_t soft, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, coeffs, batch, n, ld))) return rc;
+    if (!thresholds) return vw_fail(ctx, VW_ENULL, "thresholds cannot be null");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    int64_t nthr = per_row ? batch : 1;
+    void *pt;
+    if ((rc = vw_scratch(ctx, 5, (size_t)nthr * 8 + 64, &pt))) return rc;
+    double *thr_dev = (double *)((char *)pt + 64);
+    // thresholds are always read from the host (they come from vw_universal_threshold or the caller)
+    cudaMemcpyAsync(thr_dev, thresholds, (size_t)nthr * 8, cudaMemcpyHostToDevice, ctx->stream);
+    double *cd = coeffs;
+    if (!dev) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        cd = (double *)p;
+        if ((rc = copy_rows(ctx, cd, n, coeffs, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+    }
+    if ((rc = vw_launch_threshold(ctx, cd, batch, n, dev ? ld : n, thr_dev, per_row, soft))) return rc;
+    if (!dev) if ((rc = copy_rows(ctx, coeffs, ld, cd, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
+    return finish(ctx, flags & ~VW_FLAG_NO_SYNC, !dev);  // thresholds buffer is host memory: always complete
+}
+
+int vw_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld, double *thresholds_out,
+                           uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, w1, batch, n, ld))) return rc;
+    if (!thresholds_out) return vw_fail(ctx, VW_ENULL, "thresholds_out cannot be null");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    const double *wd = w1;
+    int64_t ldd = ld;
+    if (!dev) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, w1, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+        wd = (const double *)p;
+        ldd = n;
+    }
+    void *pt;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pt))) return rc;
+    double *thr_dev = (double *)((char *)pt + 64);
+    if ((rc = vw_launch_universal_threshold(ctx, wd, batch, n, ldd, thr_dev))) return rc;
+    cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "universal threshold");
+}
+
+int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const double *hs,
+                   const double *gs, int32_t l, int32_t levels, int32_t mode, const vw_align *align, int32_t order,
+                   double threshold, int32_t soft, double *out, int64_t ldo, double *thresholds_out, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_mode(ctx, mode))) return rc;
+    if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
+    if ((rc = check_signal_args(ctx, out, batch, n, ldo))) return rc;
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    if ((rc = check_levels(ctx, n, l, levels))) return rc;
+    if (order != VW_ORDER_SPLIT && order != VW_ORDER_PAIR) return vw_fail(ctx, VW_EINVAL, "unknown synthesis order %d", order);
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    size_t bn = (size_t)batch * (size_t)n;
+    void *pw, *pt;
+    if ((rc = vw_scratch(ctx, 3, bn * 8 * (size_t)(levels + 1), &pw))) return rc;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pt))) return rc;
+    double *wd = (double *)pw, *vd = wd + bn * (size_t)levels;
+    double *thr_dev = (double *)((char *)pt + 64);
+    const double *xd = x;
+    double *od = out;
+    int64_t ldxd = ldx, ldod = ldo;
+    if (!dev) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, bn * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, x, ldx, n, batch, cudaMemcpyHostToDevice))) return rc;
+        xd = (const double *)p; od = (double *)p; ldxd = n; ldod = n;
+    }
+    if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, batch, n, ldxd, "signal"))) return rc;
+    if ((rc = forward_device(ctx, xd, batch, n, ldxd, f, l, levels, mode, wd, n, (int64_t)bn, vd, n, flags))) return rc;
+    int per_row = 0;
+    if (threshold < 0) {
+        per_row = 1;
+        if ((rc = vw_launch_universal_threshold(ctx, wd, batch, n, n, thr_dev))) return rc;
+    } else {
+        cudaMemcpyAsync(thr_dev, &threshold, 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);  // &threshold is a stack address
+    }
+    // threshold all detail levels in place (one launch over [levels*batch] rows), then reconstruct
+    if (per_row) {
+        for (int j = 0; j < levels; j++)
+            if ((rc = vw_launch_threshold(ctx, wd + (size_t)j * bn, batch, n, n, thr_dev, 1, soft))) return rc;
+    } else if ((rc = vw_launch_threshold(ctx, wd, (int64_t)levels * batch, n, n, thr_dev, 0, soft))) return rc;
+    uint64_t mask = levels >= 64 ? ~0ull : ((1ull << levels) - 1);
+    if ((rc = inverse_device(ctx, wd, n, (int64_t)bn, vd, n, batch, n, f, l, levels, mode, align, order, mask, 1, od,
+                             ldod, flags, nullptr, 0, 0))) return rc;
+    if (!dev) if ((rc = copy_rows(ctx, out, ldo, od, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
+    if (thresholds_out) {
+        if (per_row) cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        else for (int64_t b = 0; b < batch; b++) thresholds_out[b] = threshold;
+    }
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "denoise");
+}
+
+int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
+    if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    const double *cd = c;
+    int64_t ldd = ld;
+    if (!dev) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, c, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+        cd = (const double *)p; ldd = n;
+    }
+    void *pe;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pe))) return rc;
+    double *ed = (double *)((char *)pe + 64);
+    if ((rc = vw_launch_energy(ctx, cd, batch, n, ldd, ed))) return rc;
+    cudaMemcpyAsync(out, ed, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "energy");
+}
+
+int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t n_local, const double *hs,
+                          const double *gs, int32_t l, int32_t first_level, int32_t nlevels, double *w,
+                          int64_t level_stride_w, double *vout, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
+    if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
+    if (n_local < 1) return vw_fail(ctx, VW_EEMPTY, "span cannot be empty");
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    int64_t need = vw_span_halo(l, first_level, nlevels);
+    if (need < 0) return vw_fail(ctx, VW_ELEVEL, "invalid level group [%d, %d)", first_level, first_level + nlevels);
+    if (halo < need) return vw_fail(ctx, VW_ELENGTH, "halo %lld shorter than the %lld samples levels %d..%d need",
+                                    (long long)halo, (long long)need, first_level, first_level + nlevels - 1);
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    const int64_t n_in = halo + n_local;
+    rc = VW_EUNSUPPORTED;
+    if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
+        VwFusedFwd p{vin, n_in, w, n_local, level_stride_w, vout, n_local, 1, n_in, halo, n_local,
+                     l, first_level, nlevels, VW_MODE_LINEAR};
+        rc = vw_fused_forward(ctx, p, f);
+        if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+    }
+    if (rc == VW_EUNSUPPORTED) {
+        // per-level: level i of the group must be produced on [halo - rem_i, n_in) where rem_i is the halo
+        // the later levels of the group still need
+        double *buf[2] = {nullptr, nullptr};
+        const double *cur = vin;
+        int64_t cur_off = 0;  // cur[0] is input position cur_off
+        for (int i = 0; i < nlevels; i++) {
+            int level = first_level + i;
+            int64_t d = (int64_t)1 << (level - 1);
+            int64_t rem = (i + 1 < nlevels) ? vw_span_halo(l, level + 1, nlevels - i - 1) : 0;
+            int64_t start = halo - rem;  // first position produced at this level
+            bool last = i + 1 == nlevels;
+            double *vdst;
+            if (last) vdst = vout;
+            else {
+                void *p;
+                if ((rc = vw_scratch(ctx, i & 1, (size_t)n_in * 8, &p))) return rc;
+                buf[i & 1] = (double *)p;
+                vdst = buf[i & 1];
+            }
+            // analysis over input coords: in = cur (position cur_off at index 0), outputs [start, n_in)
+            // W rows only exist for the span: write them via a second launch restricted to [halo, n_in)
+            rc = vw_launch_analysis_level(ctx, cur, 0, last ? vout : vdst, 0, last ? w + (int64_t)i * level_stride_w : nullptr,
+                                          0, n_in - cur_off, (last ? halo : start) - cur_off, last ? n_local : n_in - start,
+                                          1, f, l, d, VW_MODE_LINEAR, exact);
+            if (rc) return rc;
+            if (!last) {
+                rc = vw_launch_analysis_level(ctx, cur, 0, nullptr, 0, w + (int64_t)i * level_stride_w, 0, n_in - cur_off,
+                                              halo - cur_off, n_local, 1, f, l, d, VW_MODE_LINEAR, exact);
+                if (rc) return rc;
+                cur = vdst;
+                cur_off = start;
+            }
+        }
+    }
+    return finish(ctx, flags, false);
+}
+
+int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64_t level_stride_w, int64_t halo,
+                          int64_t n_local, const double *hs, const double *gs, int32_t l, int32_t first_level,
+                          int32_t nlevels, int32_t order, double *vout, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
+    if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
+    if (n_local < 1) return vw_fail(ctx, VW_EEMPTY, "span cannot be empty");
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    int64_t need = vw_span_halo(l, first_level, nlevels);
+    if (need < 0) return vw_fail(ctx, VW_ELEVEL, "invalid level group [%d, %d)", first_level, first_level + nlevels);
+    if (halo < need) return vw_fail(ctx, VW_ELENGTH, "halo %lld shorter than the %lld samples levels %d..%d need",
+                                    (long long)halo, (long long)need, first_level, first_level + nlevels - 1);
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    const int64_t n_in = halo + n_local;
+    rc = VW_EUNSUPPORTED;
+    if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
+        VwFusedInv p{vin, n_in, w, n_in, level_stride_w, nlevels >= 64 ? ~0ull : ((1ull << nlevels) - 1), vout, n_local,
+                     1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0};
+        rc = vw_fused_inverse(ctx, p, f);
+        if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+    }
+    if (rc == VW_EUNSUPPORTED) {
+        // per-level, top of the group first; level j output must cover [0, n_local + halo of the levels below)
+        const double *cur = vin;
+        for (int i = nlevels - 1; i >= 0; i--) {
+            int level = first_level + i;
+            int64_t d = (int64_t)1 << (level - 1);
+            int64_t below = i > 0 ? vw_span_halo(l, first_level, i) : 0;
+            int64_t n_out = n_local + below;
+            double *dst = vout;
+            if (i > 0) {
+                void *p;
+                if ((rc = vw_scratch(ctx, i & 1, (size_t)n_in * 8, &p))) return rc;
+                dst = (double *)p;
+            }
+            rc = vw_launch_synthesis_level(ctx, cur, 0, w + (int64_t)i * level_stride_w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d,
+                                           VW_MODE_LINEAR, default_align(), order == VW_ORDER_PAIR, exact);
+            if (rc) return rc;
+            cur = dst;
+        }
+    }
+    return finish(ctx, flags, false);
+}
+
+}  // extern "C"
