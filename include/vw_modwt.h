@@ -108,8 +108,10 @@ VW_API int vw_destroy(vw_ctx *ctx);
 VW_API const char *vw_last_error(const vw_ctx *ctx);
 VW_API const char *vw_status_name(int status);
 VW_API int vw_abi_version(void);
-/* Run on an existing cudaStream_t (e.g. the caller's framework stream); NULL = ctx-owned stream. */
+/* Run on an existing cudaStream_t (e.g. the caller's framework stream).  The handle is used as is, so
+ * NULL is CUDA's legacy default stream.  vw_reset_stream returns to the ctx-owned non-blocking stream. */
 VW_API int vw_set_stream(vw_ctx *ctx, void *cuda_stream);
+VW_API int vw_reset_stream(vw_ctx *ctx);
 VW_API int vw_synchronize(vw_ctx *ctx);
 VW_API int vw_device_index(const vw_ctx *ctx);
 /* Tuning knobs: "tile" (samples per CTA tile), "fuse" (max levels per launch), "threads". 0 = auto. */

@@ -1,0 +1,71 @@
+"""Developer timing helper (not the graded bench): device-resident forward / inverse GSamples/s per config."""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vectorwave_b200 as vw  # noqa: E402
+
+S = 1.0 / math.sqrt(2.0)
+CONFIGS = {
+    "c2_haar": ("haar", 4096, 4096, 4),
+    "c2_db4": ("db4", 4096, 4096, 4),
+    "c2s_db4": ("db4", 16, 4096, 4),
+    "c3_sym8": ("sym8", 1024, 65536, 8),
+    "c4_coif5": ("coif5", 1, 1 << 28, 10),
+    "c5_db8": ("db8", 256, 1 << 20, 6),
+}
+
+
+def run(name, reps, opts, mode=0):
+    wname, b, n, levels = CONFIGS[name]
+    eng = vw.Engine.get()
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    wv = vw.get_wavelet(wname)
+    hs, gs = wv.lowPassDecomposition() * S, wv.highPassDecomposition() * S
+    x = torch.randn((b, n), dtype=torch.float64, device="cuda")
+    w = torch.empty((levels, b, n), dtype=torch.float64, device="cuda")
+    v = torch.empty((b, n), dtype=torch.float64, device="cuda")
+    xr = torch.empty((b, n), dtype=torch.float64, device="cuda")
+    order = 1 if mode == 1 else 0
+    def fwd():
+        eng.forward(x, hs, gs, levels, mode, 0, w, v)
+    def inv():
+        eng.inverse(w, v, hs, gs, mode, None, order, out=xr)
+    out = {"config": name, "opts": opts, "mode": mode}
+    for label, fn in (("fwd", fwd), ("inv", inv)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[label + "_ms"] = round(ms, 4)
+        out[label + "_gsamples"] = round(b * n / ms * 1e-6, 2)
+        out[label + "_gbs_alg"] = round(24.0 * levels * b * n / ms * 1e-6, 1)
+        out[label + "_launches"] = (eng.launch_count() - l0) // reps
+    out["fwdinv_gsamples"] = round(b * n / (out["fwd_ms"] + out["inv_ms"]) * 1e-6, 2)
+    out["rt_err"] = float((xr - x).abs().max())
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2_haar,c2_db4,c3_sym8,c5_db8,c4_coif5")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--fuse", type=int, default=0)
+    ap.add_argument("--mode", type=int, default=0)
+    a = ap.parse_args()
+    for c in a.configs.split(","):
+        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse}, a.mode)

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vw_status_name": (C.c_char_p, [C.c_int]),
     "vw_abi_version": (C.c_int, []),
     "vw_set_stream": (C.c_int, [_vp, _vp]),
+    "vw_reset_stream": (C.c_int, [_vp]),
     "vw_synchronize": (C.c_int, [_vp]),
     "vw_device_index": (C.c_int, [_vp]),
     "vw_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
@@ -192,7 +193,7 @@ class Engine:
                     raise IllegalArgumentException(f"tensor on cuda:{a.device.index}, engine on cuda:{self.device}")
             self._check(self.lib.vw_set_stream(self.ctx, _vp(torch.cuda.current_stream(self.device).cuda_stream)))
             return FLAG_DEVICE_PTRS | FLAG_NO_SYNC
-        self._check(self.lib.vw_set_stream(self.ctx, None))
+        self._check(self.lib.vw_reset_stream(self.ctx))
         return 0
 
     def set_option(self, name, value):

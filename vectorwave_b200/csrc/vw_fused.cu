@@ -1,4 +1,568 @@
-// placeholder until the fused tile kernels land
+// vw_fused.cu -- the hot path: fused multi-level MODWT analysis / synthesis tile kernels for sm_100a.
+//
+// One CTA owns a tile of T output samples of one signal.  The tile plus the dilated halo the fused
+// levels need ((L-1)*2^(first-1)*(2^nlev-1) samples on the left for analysis, on the right for
+// synthesis) is staged into shared memory with TMA bulk copies (cp.async.bulk, one per contiguous
+// piece: a periodic wrap is two pieces landing on one mbarrier); zero padding and the symmetric mirror
+// are patched in shared memory.  Each level is an a-trous FIR over the resident tile: a thread produces
+// R outputs of one dilation phase (positions base + r*d), sliding one shared-memory load over up to
+// min(R,L) outputs x 2 filters of FP64 FMAs whose tap operands come straight from the constant bank.
+// R is odd, which makes the strided LDS.64 pattern bank-conflict free for every power-of-two dilation.
+// V_j stays in shared memory (ping-pong) for the next level; W_j leaves through a staging buffer and a
+// TMA bulk store (dilation < 4) or as coalesced 256-byte-per-warp stores (dilation >= 4, where lanes
+// hold consecutive samples).  Tensor cores are not used: a 2-30 tap dilated filter is not a contraction.
+//
+// Reference semantics (what is computed): CORE/modwt/MultiLevelMODWTTransform.java:244-251,710-757
+// (analysis cascade), :554-601 (synthesis cascade, PERIODIC / ZERO_PADDING), with the boundary rules of
+// CORE/internal/ScalarOps.java:700-723,790-808,818-835 and CORE/util/MathUtils.java:30-51.
+#include <algorithm>
+
 #include "vw_internal.cuh"
-int vw_fused_forward(vw_ctx *, const VwFusedFwd &, const VwFilt &) { return VW_EUNSUPPORTED; }
-int vw_fused_inverse(vw_ctx *, const VwFusedInv &, const VwFilt &) { return VW_EUNSUPPORTED; }
+
+namespace {
+
+constexpr int kR = 9;          // outputs per thread item (odd => conflict-free strided LDS.64)
+constexpr int kThreads = 256;  // threads per CTA
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copies (TMA)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completes on the mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, bulk async-group completion
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// boundary extension of one position (used only for the few out-of-range halo samples)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t wrap_mod(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
+__device__ __forceinline__ double ext_load(const double *__restrict__ row, int64_t pos, int64_t n, int mode) {
+    if (pos >= 0 && pos < n) return __ldg(row + pos);
+    if (mode == VW_PERIODIC) return __ldg(row + wrap_mod(pos, n));
+    if (mode == VW_SYMMETRIC) { int64_t m = wrap_mod(pos, 2 * n); return __ldg(row + (m < n ? m : 2 * n - 1 - m)); }
+    return 0.0;  // zero padding / linear span
+}
+
+// Stage positions [pos0, pos0+count) of `row` (length n, boundary `mode`) into dst[0..count).
+// TMA path: contiguous in-range pieces as bulk copies on `bar` (thread 0), everything else by hand.
+// Returns nothing; caller waits on `bar` (when use_tma) and __syncthreads().
+__device__ __forceinline__ void stage_tile(double *dst, const double *__restrict__ row, int64_t pos0, int count, int64_t n,
+                                           int mode, bool use_tma, uint64_t *bar, bool row_is_null) {
+    const int tid = threadIdx.x;
+    if (row_is_null) {
+        for (int i = tid; i < count; i += kThreads) dst[i] = 0.0;
+        if (use_tma && tid == 0) mbar_expect_tx(bar, 0);
+        return;
+    }
+    if (!use_tma) {
+        for (int i = tid; i < count; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
+        return;
+    }
+    if (mode == VW_PERIODIC) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)count * 8u);
+            int done = 0;
+            int64_t p = wrap_mod(pos0, n);
+            while (done < count) {
+                int64_t piece = n - p;
+                if (piece > count - done) piece = count - done;
+                bulk_g2s(dst + done, row + p, (uint32_t)piece * 8u, bar);
+                done += (int)piece;
+                p = 0;
+            }
+        }
+        return;
+    }
+    // non-periodic: one in-range piece [lo, hi), the rest (zeros or mirror) by hand
+    int64_t lo = pos0 < 0 ? 0 : pos0, hi = pos0 + count > n ? n : pos0 + count;
+    if (hi < lo) hi = lo;
+    int a = (int)(lo - pos0), b = (int)(hi - pos0);  // dst[a..b) in range
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)(b - a) * 8u);
+        if (b > a) bulk_g2s(dst + a, row + lo, (uint32_t)(b - a) * 8u, bar);
+    }
+    for (int i = tid; i < a; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
+    for (int i = b + tid; i < count; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inner products
+// ------------------------------------------------------------------------------------------------
+// analysis: out[i_r] = sum_k f[k] * in[i_r - k*d],  i_r = base + r*d.  One load feeds up to min(R,L) outputs x 2 filters.
+template <int L, int R, bool WITH_G>
+__device__ __forceinline__ void analysis_item(const double *__restrict__ in, int base, int d, int hi_clamp,
+                                              const VwFilt32 &f, double (&ah)[R], double (&ag)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
+#pragma unroll
+    for (int m = R - 1; m >= -(L - 1); m--) {  // descending m => ascending tap index per output
+        int idx = base + m * d;
+        idx = idx < hi_clamp ? idx : hi_clamp;
+        const double xv = in[idx];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r - m;
+            if (k >= 0 && k < L) {
+                ah[r] = fma(f.h[k], xv, ah[r]);
+                if (WITH_G) ag[r] = fma(f.g[k], xv, ag[r]);
+            }
+        }
+    }
+}
+
+// synthesis: acc[i_r] += sum_k f[k] * in[i_r + k*d]
+template <int L, int R>
+__device__ __forceinline__ void synthesis_item(const double *__restrict__ in, int base, int d, int hi_clamp,
+                                               const double (&taps)[VW_FUSED_MAX_L], double (&acc)[R]) {
+#pragma unroll
+    for (int m = 0; m <= R + L - 2; m++) {  // ascending m => ascending tap index per output
+        int idx = base + m * d;
+        idx = idx < hi_clamp ? idx : hi_clamp;
+        const double xv = in[idx];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = m - r;
+            if (k >= 0 && k < L) acc[r] = fma(taps[k], xv, acc[r]);
+        }
+    }
+}
+
+// runtime-L variants (filter lengths without a specialisation, L <= 32)
+template <int R, bool WITH_G>
+__device__ __forceinline__ void analysis_item_dyn(const double *__restrict__ in, int base, int d, int hi_clamp, int L,
+                                                  const VwFilt32 &f, double (&ah)[R], double (&ag)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
+    for (int k = 0; k < L; k++) {
+        const double hk = f.h[k], gk = f.g[k];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int idx = base + (r - k) * d;
+            idx = idx < hi_clamp ? idx : hi_clamp;
+            const double xv = in[idx];
+            ah[r] = fma(hk, xv, ah[r]);
+            if (WITH_G) ag[r] = fma(gk, xv, ag[r]);
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ void synthesis_item_dyn(const double *__restrict__ in, int base, int d, int hi_clamp, int L,
+                                                   const double (&taps)[VW_FUSED_MAX_L], double (&acc)[R]) {
+    for (int k = 0; k < L; k++) {
+        const double tk = taps[k];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int idx = base + (r + k) * d;
+            idx = idx < hi_clamp ? idx : hi_clamp;
+            acc[r] = fma(tk, in[idx], acc[r]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const double *x; long long ldx;
+    double *w; long long ldw, lsw;
+    double *v; long long ldv;
+    long long n_in, t0, n_out, batch;
+    int tile, htot, slack, nlev, log2d0, mode, tiles_per_row, use_tma, use_stage, lrt;
+    VwFilt32 f;
+};
+
+struct InvArgs {
+    const double *v; long long ldv;
+    const double *w; long long ldw, lsw;
+    double *out; long long ldo;
+    unsigned long long detail_mask;
+    long long n_in, n_out, batch;
+    int tile, htot, nlev, log2d0, mode, tiles_per_row, use_tma, lrt;
+    const double *thr; int thr_per_row, thr_soft;
+    VwFilt32 f;
+};
+
+// ------------------------------------------------------------------------------------------------
+// fused analysis
+// ------------------------------------------------------------------------------------------------
+// shared memory: [bufA: P][bufB: P][S0: T][S1: T] doubles (S only when use_stage), then one mbarrier
+template <int L>
+__global__ void __launch_bounds__(kThreads) k_fused_analysis(const __grid_constant__ FwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int LR = L > 0 ? L : a.lrt;  // runtime filter length
+    const int T = a.tile, HT = a.htot, P = T + HT;
+    double *buf0 = reinterpret_cast<double *>(smem_raw);
+    double *buf1 = buf0 + P;
+    double *stg0 = buf1 + P;
+    double *stg1 = stg0 + (a.use_stage ? T : 0);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stg1 + (a.use_stage ? T : 0));
+
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.x / a.tiles_per_row;
+    const int tile = blockIdx.x % a.tiles_per_row;
+    const long long g0 = a.t0 + (long long)tile * T;            // first owned position (input coordinates)
+    long long rem = a.t0 + a.n_out - g0;
+    const int Tt = (int)(rem < T ? rem : T);                     // owned samples in this tile
+    const int PP = HT + Tt;                                      // valid extent of the tile buffers
+    const double *xrow = a.x + b * a.ldx;
+
+    if (a.use_tma && tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    stage_tile(buf0, xrow, g0 - HT, PP, a.n_in, a.mode, a.use_tma, bar, false);
+    if (a.use_tma) mbar_wait(bar, 0);
+    __syncthreads();
+
+    double *cur = buf0, *nxt = buf1;
+    int lo_prev = 0;
+    int pending_stage = 0;  // bulk stores issued from staging buffers so far (thread 0 bookkeeping only)
+    for (int lev = 0; lev < a.nlev; lev++) {
+        const int ld2 = a.log2d0 + lev;
+        const int d = 1 << ld2;
+        const int H = (LR - 1) << ld2;
+        const bool last = lev + 1 == a.nlev;
+        const int lo_cur = (lev == 0 ? a.slack : lo_prev) + H;   // first index where V_lev is defined
+        const bool staged = a.use_stage && d < 4;
+        double *stg = (lev & 1) ? stg1 : stg0;
+        double *wrow = a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0);  // W_lev[owned region]
+
+        // part 0: halo region [lo_cur, HT) -- approximation only (not needed after the last level)
+        // part 1: owned region [HT, PP) -- approximation and detail
+        for (int part = last ? 1 : 0; part < 2; part++) {
+            const int ra = part == 0 ? lo_cur : HT, rb = part == 0 ? HT : PP;
+            const int M = rb - ra;
+            if (M <= 0) continue;
+            const int Q = (M + d - 1) >> ld2;                  // samples per phase (max)
+            const int items = ((Q + kR - 1) / kR) << ld2;      // chunks x phases
+            for (int wi = tid; wi < items; wi += kThreads) {
+                const int c = wi >> ld2, ph = wi & (d - 1);
+                const int base = ra + ((c * kR) << ld2) + ph;
+                if (base >= rb) continue;
+                double ah[kR], ag[kR];
+                if (part == 0) {
+                    if (L > 0) analysis_item<(L > 0 ? L : 2), kR, false>(cur, base, d, PP - 1, a.f, ah, ag);
+                    else analysis_item_dyn<kR, false>(cur, base, d, PP - 1, LR, a.f, ah, ag);
+                } else {
+                    if (L > 0) analysis_item<(L > 0 ? L : 2), kR, true>(cur, base, d, PP - 1, a.f, ah, ag);
+                    else analysis_item_dyn<kR, true>(cur, base, d, PP - 1, LR, a.f, ah, ag);
+                }
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int i = base + (r << ld2);
+                    if (i < rb) {
+                        nxt[i] = ah[r];
+                        if (part == 1) {
+                            if (staged) stg[i - HT] = ag[r];
+                            else wrow[i - HT] = ag[r];
+                        }
+                    }
+                }
+            }
+        }
+        fence_async_smem();   // generic-proxy writes of nxt / stg must be visible to the bulk-store (async) proxy
+        __syncthreads();
+        // SYMMETRIC: V_lev at positions < 0 is the mirror of V_lev itself (ScalarOps.java:818-835 applied per level)
+        if (a.mode == VW_SYMMETRIC && !last && g0 - HT < 0) {
+            const int neg = (int)(HT - g0);                     // tile indices [0, neg) are positions < 0
+            for (int i = lo_cur + tid; i < neg; i += kThreads) {
+                const long long pos = g0 - HT + i;              // negative
+                nxt[i] = nxt[(int)((-1 - pos) - (g0 - HT))];
+            }
+            __syncthreads();
+        }
+        if (staged) {
+            if (a.use_tma) {
+                if (tid == 0) {
+                    bulk_s2g(wrow, stg, (uint32_t)Tt * 8u);
+                    bulk_commit();
+                    pending_stage++;
+                    bulk_wait_read<1>();  // the other staging buffer is free again before anyone writes it
+                }
+            } else {
+                for (int i = tid; i < Tt; i += kThreads) wrow[i] = stg[i];
+            }
+            __syncthreads();
+        }
+        double *t = cur; cur = nxt; nxt = t;
+        lo_prev = lo_cur;
+    }
+    // V after the last level sits in cur[HT .. HT+Tt)
+    double *vrow = a.v + b * a.ldv + (g0 - a.t0);
+    if (a.use_tma) {
+        if (tid == 0) {
+            bulk_s2g(vrow, cur + HT, (uint32_t)Tt * 8u);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else {
+        for (int i = tid; i < Tt; i += kThreads) vrow[i] = cur[HT + i];
+    }
+    (void)pending_stage;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused synthesis (index rule t + k*d: PERIODIC, ZERO_PADDING, linear span)
+// ------------------------------------------------------------------------------------------------
+// shared memory: [bufA: P][bufB: P][W0: P][W1: P] doubles, then three mbarriers (V, W0, W1)
+template <int L>
+__global__ void __launch_bounds__(kThreads) k_fused_synthesis(const __grid_constant__ InvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int LR = L > 0 ? L : a.lrt;
+    const int T = a.tile, HT = a.htot, P = T + HT;
+    double *buf0 = reinterpret_cast<double *>(smem_raw);
+    double *buf1 = buf0 + P;
+    double *wb0 = buf1 + P, *wb1 = buf1 + 2 * P;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(buf1 + 3 * P);  // [0]=V, [1]=W0, [2]=W1
+
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.x / a.tiles_per_row;
+    const int tile = blockIdx.x % a.tiles_per_row;
+    const long long g0 = (long long)tile * T;
+    long long rem = a.n_out - g0;
+    const int Tt = (int)(rem < T ? rem : T);
+
+    if (a.use_tma && tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // extent of level j's inputs: Tt + sum of H over the group's levels <= j
+    auto extent = [&](int lev) {  // lev = index inside the group, 0 = finest
+        return Tt + (int)(((long long)(LR - 1) << a.log2d0) * ((1ll << (lev + 1)) - 1));
+    };
+    const int top = a.nlev - 1;
+    const double *vrow = a.v ? a.v + b * a.ldv : nullptr;
+    auto stage_count = [&](int lev) { int e = extent(lev); return a.use_tma ? ((e + 1) & ~1) : e; };  // bulk copies move 16-byte units
+    stage_tile(buf0, vrow, g0, stage_count(top), a.n_in, a.mode, a.use_tma, &bars[0], vrow == nullptr);
+    auto stage_w = [&](int lev, int slot) {
+        const bool have = (a.detail_mask >> lev) & 1ull;
+        const double *wrow = have ? a.w + (long long)lev * a.lsw + b * a.ldw : nullptr;
+        stage_tile(slot ? wb1 : wb0, wrow, g0, stage_count(lev), a.n_in, a.mode, a.use_tma, &bars[1 + slot], !have);
+    };
+    stage_w(top, top & 1);
+    if (a.use_tma) mbar_wait(&bars[0], 0);
+    uint32_t wphase0 = 0, wphase1 = 0;
+
+    double *cur = buf0, *nxt = buf1;
+    for (int lev = top; lev >= 0; lev--) {
+        const int slot = lev & 1;
+        if (lev > 0) stage_w(lev - 1, slot ^ 1);   // prefetch the next level's details while this one computes
+        if (a.use_tma) {
+            if (slot) { mbar_wait(&bars[2], wphase1); wphase1 ^= 1; }
+            else { mbar_wait(&bars[1], wphase0); wphase0 ^= 1; }
+        }
+        __syncthreads();
+        const bool have_w = (a.detail_mask >> lev) & 1ull;
+        double *wt = slot ? wb1 : wb0;
+        const int in_ext = extent(lev);
+        if (a.thr && have_w) {
+            // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118)
+            const double lam = a.thr[a.thr_per_row ? b : 0];
+            for (int i = tid; i < in_ext; i += kThreads) {
+                const double c = wt[i], ab = fabs(c), m = ab - lam;
+                double r;
+                if (a.thr_soft) r = ab > lam ? (c > 0.0 ? m : (c < 0.0 ? -m : c * m)) : 0.0;
+                else r = ab <= lam ? 0.0 : c;
+                wt[i] = r;
+            }
+            __syncthreads();
+        }
+        const int ld2 = a.log2d0 + lev;
+        const int d = 1 << ld2;
+        const int M = lev > 0 ? extent(lev - 1) : Tt;           // outputs of this level
+        const int Q = (M + d - 1) >> ld2;
+        const int items = ((Q + kR - 1) / kR) << ld2;
+        for (int wi = tid; wi < items; wi += kThreads) {
+            const int c = wi >> ld2, ph = wi & (d - 1);
+            const int base = ((c * kR) << ld2) + ph;
+            if (base >= M) continue;
+            double acc[kR];
+#pragma unroll
+            for (int r = 0; r < kR; r++) acc[r] = 0.0;
+            if (L > 0) {
+                synthesis_item<(L > 0 ? L : 2), kR>(cur, base, d, in_ext - 1, a.f.h, acc);
+                if (have_w) synthesis_item<(L > 0 ? L : 2), kR>(wt, base, d, in_ext - 1, a.f.g, acc);
+            } else {
+                synthesis_item_dyn<kR>(cur, base, d, in_ext - 1, LR, a.f.h, acc);
+                if (have_w) synthesis_item_dyn<kR>(wt, base, d, in_ext - 1, LR, a.f.g, acc);
+            }
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+                const int i = base + (r << ld2);
+                if (i < M) nxt[i] = acc[r];
+            }
+        }
+        fence_async_smem();   // order this level's generic-proxy traffic before later bulk copies touch the buffers
+        __syncthreads();
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    double *orow = a.out + b * a.ldo + g0;
+    if (a.use_tma) {
+        if (tid == 0) {
+            bulk_s2g(orow, cur, (uint32_t)Tt * 8u);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else {
+        for (int i = tid; i < Tt; i += kThreads) orow[i] = cur[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int ilog2(int64_t v) { int r = 0; while ((1ll << r) < v) r++; return r; }
+
+template <typename K>
+int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
+    return vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                         "cudaFuncSetAttribute(max dynamic smem)");
+}
+
+#define VW_DISPATCH_L(L, CALL)            \
+    switch (L) {                          \
+        case 2: CALL(2); break;           \
+        case 4: CALL(4); break;           \
+        case 6: CALL(6); break;           \
+        case 8: CALL(8); break;           \
+        case 10: CALL(10); break;         \
+        case 12: CALL(12); break;         \
+        case 16: CALL(16); break;         \
+        case 18: CALL(18); break;         \
+        case 20: CALL(20); break;         \
+        case 30: CALL(30); break;         \
+        default: CALL(0); break;          \
+    }
+
+}  // namespace
+
+int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
+    if (p.l < 2 || p.l > VW_FUSED_MAX_L || p.nlevels < 1 || p.batch < 1 || p.n_out < 1) return VW_EUNSUPPORTED;
+    const int64_t d0 = 1ll << (p.first_level - 1);
+    const int64_t hexact = (int64_t)(p.l - 1) * d0 * ((1ll << p.nlevels) - 1);
+    const int64_t htot = (hexact + 1) & ~1ll;
+    if (hexact > p.n_in || htot > 24576) return VW_EUNSUPPORTED;
+    if (p.first_level + p.nlevels - 1 > 30) return VW_EUNSUPPORTED;
+    const bool use_stage = d0 < 4;
+    const bool use_tma = aligned16(p.x) && aligned16(p.w) && aligned16(p.v) && !(p.ldx & 1) && !(p.ldw & 1) &&
+                         !(p.lsw & 1) && !(p.ldv & 1) && !(p.n_in & 1) && !(p.t0 & 1) && !(p.n_out & 1);
+    // tile: as many owned samples as keep every level of the group within one item per thread, within smem
+    const size_t smem_cap = ctx->smem_optin - 1024;
+    int64_t tile = ctx->opt_tile > 0 ? ctx->opt_tile : (int64_t)kR * kThreads - (htot - (int64_t)(p.l - 1) * d0);
+    if (tile < htot) tile = htot;            // the symmetric mirror patch needs the sources inside the tile
+    if (tile < 512) tile = 512;
+    auto smem_for = [&](int64_t t) { return (size_t)((2 * (t + htot) + (use_stage ? 2 * t : 0)) * 8 + 64); };
+    while (smem_for(tile) > smem_cap && tile > 512) tile -= 256;
+    if (smem_for(tile) > smem_cap || tile < htot) return VW_EUNSUPPORTED;
+    tile &= ~1ll;
+    if (ctx->opt_tile <= 0) {  // equal tiles: ceil(n_out / ntiles), even
+        int64_t nt = (p.n_out + tile - 1) / tile;
+        int64_t bal = (((p.n_out + nt - 1) / nt) + 1) & ~1ll;
+        if (bal >= htot || p.mode != VW_SYMMETRIC) tile = bal;
+    }
+    if (tile > p.n_out) tile = (p.n_out + 1) & ~1ll;
+    if (p.mode == VW_SYMMETRIC && (p.n_in < htot || tile < htot)) return VW_EUNSUPPORTED;
+    const int64_t tiles_per_row = (p.n_out + tile - 1) / tile;
+    if (tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
+
+    FwdArgs a;
+    a.x = p.x; a.ldx = p.ldx; a.w = p.w; a.ldw = p.ldw; a.lsw = p.lsw; a.v = p.v; a.ldv = p.ldv;
+    a.n_in = p.n_in; a.t0 = p.t0; a.n_out = p.n_out; a.batch = p.batch;
+    a.tile = (int)tile; a.htot = (int)htot; a.slack = (int)(htot - hexact); a.nlev = p.nlevels;
+    a.log2d0 = p.first_level - 1; a.mode = p.mode; a.tiles_per_row = (int)tiles_per_row;
+    a.use_tma = use_tma; a.use_stage = use_stage; a.lrt = p.l;
+    for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
+    const size_t smem = smem_for(tile);
+    const unsigned grid = (unsigned)(tiles_per_row * p.batch);
+    int rc = VW_OK;
+#define VW_FWD_CALL(LL)                                                                    \
+    do {                                                                                   \
+        if ((rc = set_smem(ctx, k_fused_analysis<LL>, smem))) return rc;                   \
+        k_fused_analysis<LL><<<grid, kThreads, smem, ctx->stream>>>(a);                    \
+    } while (0)
+    VW_DISPATCH_L(p.l, VW_FWD_CALL)
+#undef VW_FWD_CALL
+    ctx->launches++;
+    return vw_cuda_check(ctx, cudaGetLastError(), "fused analysis launch");
+}
+
+int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
+    if (p.l < 2 || p.l > VW_FUSED_MAX_L || p.nlevels < 1 || p.batch < 1 || p.n_out < 1) return VW_EUNSUPPORTED;
+    if (p.mode == VW_SYMMETRIC) return VW_EUNSUPPORTED;  // two-sided alignment: per-level kernels
+    const int64_t d0 = 1ll << (p.first_level - 1);
+    const int64_t hexact = (int64_t)(p.l - 1) * d0 * ((1ll << p.nlevels) - 1);
+    const int64_t htot = (hexact + 1) & ~1ll;
+    if (hexact > p.n_in || htot > 12288) return VW_EUNSUPPORTED;
+    if (p.first_level + p.nlevels - 1 > 30) return VW_EUNSUPPORTED;
+    const bool use_tma = (!p.v || aligned16(p.v)) && aligned16(p.w) && aligned16(p.out) && !(p.ldv & 1) && !(p.ldw & 1) &&
+                         !(p.lsw & 1) && !(p.ldo & 1) && !(p.n_in & 1) && !(p.n_out & 1);
+    const size_t smem_cap = ctx->smem_optin - 1024;
+    int64_t tile = ctx->opt_tile > 0 ? ctx->opt_tile : (int64_t)kR * kThreads - htot;
+    if (tile < 512) tile = 512;
+    auto smem_for = [&](int64_t t) { return (size_t)(4 * (t + htot) * 8 + 64); };
+    while (smem_for(tile) > smem_cap && tile > 512) tile -= 256;
+    if (smem_for(tile) > smem_cap) return VW_EUNSUPPORTED;
+    tile &= ~1ll;
+    if (ctx->opt_tile <= 0) {
+        int64_t nt = (p.n_out + tile - 1) / tile;
+        tile = (((p.n_out + nt - 1) / nt) + 1) & ~1ll;
+    }
+    if (tile > p.n_out) tile = (p.n_out + 1) & ~1ll;
+    const int64_t tiles_per_row = (p.n_out + tile - 1) / tile;
+    if (tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
+
+    InvArgs a;
+    a.v = p.v; a.ldv = p.ldv; a.w = p.w; a.ldw = p.ldw; a.lsw = p.lsw; a.out = p.out; a.ldo = p.ldo;
+    a.detail_mask = p.detail_mask; a.n_in = p.n_in; a.n_out = p.n_out; a.batch = p.batch;
+    a.tile = (int)tile; a.htot = (int)htot; a.nlev = p.nlevels; a.log2d0 = p.first_level - 1; a.mode = p.mode;
+    a.tiles_per_row = (int)tiles_per_row; a.use_tma = use_tma; a.lrt = p.l;
+    a.thr = p.thr_dev; a.thr_per_row = p.thr_per_row; a.thr_soft = p.thr_soft;
+    for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
+    const size_t smem = smem_for(tile);
+    const unsigned grid = (unsigned)(tiles_per_row * p.batch);
+    int rc = VW_OK;
+#define VW_INV_CALL(LL)                                                                    \
+    do {                                                                                   \
+        if ((rc = set_smem(ctx, k_fused_synthesis<LL>, smem))) return rc;                  \
+        k_fused_synthesis<LL><<<grid, kThreads, smem, ctx->stream>>>(a);                   \
+    } while (0)
+    VW_DISPATCH_L(p.l, VW_INV_CALL)
+#undef VW_INV_CALL
+    ctx->launches++;
+    return vw_cuda_check(ctx, cudaGetLastError(), "fused synthesis launch");
+}

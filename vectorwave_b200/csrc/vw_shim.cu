@@ -162,21 +162,25 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
     int level = 1, pp = 0;
     while (level <= levels) {
         int rc;
-        int nf = allow_fused ? fuse_depth(ctx, l, level, levels - level + 1, n) : 1;
-        bool last = level + nf - 1 == levels;
-        double *vout = vj;
-        int64_t ld_vout = ldv;
-        if (!last) {
+        // destination of the approximation leaving a group that ends at level `end`
+        auto pick_out = [&](int end, double *&vout, int64_t &ld_vout) -> int {
+            if (end == levels) { vout = vj; ld_vout = ldv; return VW_OK; }
             if (!buf[pp]) {
                 void *p;
-                if ((rc = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p))) return rc;
+                int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
+                if (r) return r;
                 buf[pp] = (double *)p;
             }
             vout = buf[pp];
             ld_vout = n;
-        }
+            return VW_OK;
+        };
+        int nf = allow_fused ? fuse_depth(ctx, l, level, levels - level + 1, n) : 1;
+        double *vout = nullptr;
+        int64_t ld_vout = 0;
         rc = VW_EUNSUPPORTED;
         if (allow_fused) {
+            if ((rc = pick_out(level + nf - 1, vout, ld_vout))) return rc;
             VwFusedFwd p{cur, ld_cur, w + (int64_t)(level - 1) * lsw, ldw, lsw, vout, ld_vout, batch, n, 0, n,
                          l, level, nf, mode};
             rc = vw_fused_forward(ctx, p, f);
@@ -184,8 +188,7 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
         }
         if (rc == VW_EUNSUPPORTED) {
             nf = 1;
-            last = level == levels;
-            if (last) { vout = vj; ld_vout = ldv; }
+            if ((rc = pick_out(level, vout, ld_vout))) return rc;
             rc = vw_launch_analysis_level(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n, 0, n,
                                           batch, f, l, (int64_t)1 << (level - 1), mode, exact);
             if (rc) return rc;
@@ -229,21 +232,24 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 nf--;
             }
         }
-        int first = level - nf + 1;
-        bool last = first == 1;
-        double *out = xout;
-        int64_t ld_out = ldx;
-        if (!last) {
+        auto pick_out = [&](int first, double *&out, int64_t &ld_out) -> int {
+            if (first == 1) { out = xout; ld_out = ldx; return VW_OK; }
             if (!buf[pp]) {
                 void *p;
-                if ((rc = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p))) return rc;
+                int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
+                if (r) return r;
                 buf[pp] = (double *)p;
             }
             out = buf[pp];
             ld_out = n;
-        }
+            return VW_OK;
+        };
+        double *out = nullptr;
+        int64_t ld_out = 0;
         rc = VW_EUNSUPPORTED;
         if (allow_fused) {
+            int first = level - nf + 1;
+            if ((rc = pick_out(first, out, ld_out))) return rc;
             VwFusedInv p{cur, ld_cur, w + (int64_t)(first - 1) * lsw, ldw, lsw,
                          (detail_mask >> (first - 1)) & ((nf >= 64 ? ~0ull : ((1ull << nf) - 1))),
                          out, ld_out, batch, n, n, l, first, nf, mode, thr_dev, thr_per_row, thr_soft};
@@ -252,9 +258,7 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
         }
         if (rc == VW_EUNSUPPORTED) {
             nf = 1;
-            first = level;
-            last = first == 1;
-            if (last) { out = xout; ld_out = ldx; }
+            if ((rc = pick_out(level, out, ld_out))) return rc;
             vw_align al = align ? align[level - 1] : default_align();
             const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
             if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
@@ -342,7 +346,13 @@ const char *vw_last_error(const vw_ctx *ctx) { return ctx ? ctx->err.c_str() : "
 
 int vw_set_stream(vw_ctx *ctx, void *s) {
     if (!ctx) return VW_ENULL;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;
+    return VW_OK;
+}
+
+int vw_reset_stream(vw_ctx *ctx) {
+    if (!ctx) return VW_ENULL;
+    ctx->stream = ctx->own_stream;
     return VW_OK;
 }
 
