@@ -116,6 +116,11 @@ VW_API int vw_synchronize(vw_ctx *ctx);
 VW_API int vw_device_index(const vw_ctx *ctx);
 /* Tuning knobs: "tile" (samples per CTA tile), "fuse" (max levels per launch), "threads". 0 = auto. */
 VW_API int vw_set_option(vw_ctx *ctx, const char *name, int64_t value);
+/* Writes the level schedule the engine would use (which levels share one fused launch, tile sizes, modelled
+ * cycles/sample) as text into out[0..cap).  Pure host logic: needs no device (assumes 227 KB shared memory per CTA).
+ * forward != 0: analysis; else synthesis.  Returns the number of launch groups, or a negative vw_status. */
+VW_API int vw_describe_plan(int forward, int32_t l, int32_t levels, int64_t n, int64_t tile, int32_t fuse, char *out,
+                            size_t cap);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 VW_API int64_t vw_launch_count(const vw_ctx *ctx);
 

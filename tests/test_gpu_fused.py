@@ -224,3 +224,25 @@ def test_full_size_properties_periodic(eng, name, b, n, levels, rt_tol):
     wy, vy = eng.forward(y, hs, gs, levels, 0)
     wz, vz = eng.forward(2.0 * x[:1] + 3.0 * y, hs, gs, levels, 0)
     assert float((wz - (2.0 * w[:, :1] + 3.0 * wy)).abs().max()) <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("name,n,levels", [("haar", 20000, 9), ("db4", 30001, 8), ("sym8", 40000, 8), ("coif5", 65536, 8),
+                                           ("db6", 9000, 7)])
+def test_deep_levels_column_kernels(eng, mode, name, n, levels):
+    """Levels >= 6 (dilation >= 32) run on the register-sliding-window column kernels, all boundary modes,
+    including the SYMMETRIC synthesis with its per-level (sigma, tau) alignment."""
+    from vectorwave_b200.modwt import multilevel_alignment
+    rng = np.random.default_rng(n + mode)
+    x = rng.standard_normal((2, n))
+    h, g, wid = filters(name)
+    w, v = _check_forward(eng, x, name, levels, mode)
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(vw.get_wavelet(name), bm, levels)
+    xr = np.asarray(eng.inverse(w, v, h * S, g * S, mode, align, order))
+    for i in range(2):
+        ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, wid)
+        np.testing.assert_allclose(xr[i], ref, rtol=0, atol=tol(x))
+    # the column kernels must agree with the per-level kernels they replace
+    w2, v2 = eng.forward(x, h * S, g * S, levels, mode, _native.FLAG_NO_FUSE)
+    np.testing.assert_allclose(w, w2, rtol=0, atol=1e-13)

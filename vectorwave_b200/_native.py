@@ -60,6 +60,7 @@ SIGNATURES = {
     "vw_device_index": (C.c_int, [_vp]),
     "vw_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "vw_launch_count": (_i64, [_vp]),
+    "vw_describe_plan": (C.c_int, [C.c_int, _i32, _i32, _i64, _i64, _i32, C.c_char_p, C.c_size_t]),
     "vw_alloc_pinned": (_vp, [C.c_size_t]),
     "vw_free_pinned": (None, [_vp]),
     "vw_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -102,6 +103,15 @@ def load_library():
                 fn.argtypes = args
             _lib = lib
     return _lib
+
+
+def describe_plan(forward, l, levels, n, tile=0, fuse=0):
+    """Text of the level schedule (host logic only; works without a GPU)."""
+    buf = C.create_string_buffer(4096)
+    rc = load_library().vw_describe_plan(int(bool(forward)), int(l), int(levels), int(n), int(tile), int(fuse), buf, 4096)
+    if rc < 0:
+        raise IllegalArgumentException(f"vw_describe_plan failed: {rc}")
+    return buf.value.decode()
 
 
 def _is_torch(x):
@@ -195,6 +205,20 @@ class Engine:
             return FLAG_DEVICE_PTRS | FLAG_NO_SYNC
         self._check(self.lib.vw_reset_stream(self.ctx))
         return 0
+
+    def pinned_empty(self, shape):
+        """float64 numpy array over page-locked host memory (vw_alloc_pinned): the host side of asynchronous
+        DMA, what the Java binding exposes as MemorySegment.reinterpret.  Freed when the array is collected."""
+        count = int(np.prod(shape))
+        ptr = self.lib.vw_alloc_pinned(max(count, 1) * 8)
+        if not ptr:
+            raise NativeEngineError("vw_alloc_pinned failed")
+        buf = (C.c_double * max(count, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.float64, count=count).reshape(shape)
+        lib = self.lib
+        import weakref
+        weakref.finalize(buf, lib.vw_free_pinned, ptr)
+        return arr
 
     def set_option(self, name, value):
         self._check(self.lib.vw_set_option(self.ctx, name.encode(), int(value)))

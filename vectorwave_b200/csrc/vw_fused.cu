@@ -15,7 +15,10 @@
 // Reference semantics (what is computed): CORE/modwt/MultiLevelMODWTTransform.java:244-251,710-757
 // (analysis cascade), :554-601 (synthesis cascade, PERIODIC / ZERO_PADDING), with the boundary rules of
 // CORE/internal/ScalarOps.java:700-723,790-808,818-835 and CORE/util/MathUtils.java:30-51.
+#include <math.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "vw_internal.cuh"
 
@@ -121,17 +124,21 @@ __device__ __forceinline__ void stage_tile(double *dst, const double *__restrict
 // ------------------------------------------------------------------------------------------------
 // inner products
 // ------------------------------------------------------------------------------------------------
-// analysis: out[i_r] = sum_k f[k] * in[i_r - k*d],  i_r = base + r*d.  One load feeds up to min(R,L) outputs x 2 filters.
-template <int L, int R, bool WITH_G>
-__device__ __forceinline__ void analysis_item(const double *__restrict__ in, int base, int d, int hi_clamp,
-                                              const VwFilt32 &f, double (&ah)[R], double (&ag)[R]) {
+// analysis: out[i_r] = sum_k f[k] * in[i_r - k*d],  i_r = base + r*d.  One load feeds up to min(R,L) outputs x 2
+// filters.  `top` points at in[base + (R-1)*d]; the window is walked downwards with one pointer step per load.
+// FULL == false: only the first `nvalid` outputs exist; loads that would only feed the others are skipped.
+template <int L, int R, bool WITH_G, bool FULL>
+__device__ __forceinline__ void analysis_item(const double *__restrict__ top, int d, int nvalid, const VwFilt32 &f,
+                                              double (&ah)[R], double (&ag)[R]) {
 #pragma unroll
     for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
+    const double *p = top;
 #pragma unroll
     for (int m = R - 1; m >= -(L - 1); m--) {  // descending m => ascending tap index per output
-        int idx = base + m * d;
-        idx = idx < hi_clamp ? idx : hi_clamp;
-        const double xv = in[idx];
+        double xv;
+        if (FULL || m <= 0) xv = *p;
+        else xv = m < nvalid ? *p : 0.0;
+        p -= d;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k = r - m;
@@ -143,15 +150,17 @@ __device__ __forceinline__ void analysis_item(const double *__restrict__ in, int
     }
 }
 
-// synthesis: acc[i_r] += sum_k f[k] * in[i_r + k*d]
-template <int L, int R>
-__device__ __forceinline__ void synthesis_item(const double *__restrict__ in, int base, int d, int hi_clamp,
+// synthesis: acc[i_r] += sum_k taps[k] * in[i_r + k*d]; `bot` points at in[base]
+template <int L, int R, bool FULL>
+__device__ __forceinline__ void synthesis_item(const double *__restrict__ bot, int d, int nvalid,
                                                const double (&taps)[VW_FUSED_MAX_L], double (&acc)[R]) {
+    const double *p = bot;
 #pragma unroll
     for (int m = 0; m <= R + L - 2; m++) {  // ascending m => ascending tap index per output
-        int idx = base + m * d;
-        idx = idx < hi_clamp ? idx : hi_clamp;
-        const double xv = in[idx];
+        double xv;
+        if (FULL || m < L) xv = *p;
+        else xv = m < nvalid + L - 1 ? *p : 0.0;
+        p += d;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k = m - r;
@@ -220,7 +229,7 @@ struct InvArgs {
 // ------------------------------------------------------------------------------------------------
 // shared memory: [bufA: P][bufB: P][S0: T][S1: T] doubles (S only when use_stage), then one mbarrier
 template <int L>
-__global__ void __launch_bounds__(kThreads) k_fused_analysis(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_analysis(const __grid_constant__ FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;  // runtime filter length
     const int T = a.tile, HT = a.htot, P = T + HT;
@@ -270,22 +279,41 @@ __global__ void __launch_bounds__(kThreads) k_fused_analysis(const __grid_consta
                 const int c = wi >> ld2, ph = wi & (d - 1);
                 const int base = ra + ((c * kR) << ld2) + ph;
                 if (base >= rb) continue;
+                const int nvalid = min(kR, (rb - base + d - 1) >> ld2);
+                const bool full = nvalid == kR;
+                const double *top = cur + base + ((kR - 1) << ld2);
                 double ah[kR], ag[kR];
-                if (part == 0) {
-                    if (L > 0) analysis_item<(L > 0 ? L : 2), kR, false>(cur, base, d, PP - 1, a.f, ah, ag);
-                    else analysis_item_dyn<kR, false>(cur, base, d, PP - 1, LR, a.f, ah, ag);
+                if (L > 0) {
+                    constexpr int LL = L > 0 ? L : 2;
+                    if (part == 0) {
+                        if (full) analysis_item<LL, kR, false, true>(top, d, nvalid, a.f, ah, ag);
+                        else analysis_item<LL, kR, false, false>(top, d, nvalid, a.f, ah, ag);
+                    } else {
+                        if (full) analysis_item<LL, kR, true, true>(top, d, nvalid, a.f, ah, ag);
+                        else analysis_item<LL, kR, true, false>(top, d, nvalid, a.f, ah, ag);
+                    }
                 } else {
-                    if (L > 0) analysis_item<(L > 0 ? L : 2), kR, true>(cur, base, d, PP - 1, a.f, ah, ag);
+                    if (part == 0) analysis_item_dyn<kR, false>(cur, base, d, PP - 1, LR, a.f, ah, ag);
                     else analysis_item_dyn<kR, true>(cur, base, d, PP - 1, LR, a.f, ah, ag);
                 }
+                double *q = nxt + base;
+                if (part == 0) {
 #pragma unroll
-                for (int r = 0; r < kR; r++) {
-                    const int i = base + (r << ld2);
-                    if (i < rb) {
-                        nxt[i] = ah[r];
-                        if (part == 1) {
-                            if (staged) stg[i - HT] = ag[r];
-                            else wrow[i - HT] = ag[r];
+                    for (int r = 0; r < kR; r++) { if (full || r < nvalid) *q = ah[r]; q += d; }
+                } else {
+                    if (staged) {
+                        double *wq = stg + (base - HT);
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            if (full || r < nvalid) { *q = ah[r]; *wq = ag[r]; }
+                            q += d; wq += d;
+                        }
+                    } else {
+                        double *wq = wrow + (base - HT);
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            if (full || r < nvalid) { *q = ah[r]; *wq = ag[r]; }
+                            q += d; wq += d;
                         }
                     }
                 }
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(kThreads) k_fused_analysis(const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // shared memory: [bufA: P][bufB: P][W0: P][W1: P] doubles, then three mbarriers (V, W0, W1)
 template <int L>
-__global__ void __launch_bounds__(kThreads) k_fused_synthesis(const __grid_constant__ InvArgs a) {
+__global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_synthesis(const __grid_constant__ InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;
     const int T = a.tile, HT = a.htot, P = T + HT;
@@ -409,21 +437,27 @@ __global__ void __launch_bounds__(kThreads) k_fused_synthesis(const __grid_const
             const int c = wi >> ld2, ph = wi & (d - 1);
             const int base = ((c * kR) << ld2) + ph;
             if (base >= M) continue;
+            const int nvalid = min(kR, (M - base + d - 1) >> ld2);
+            const bool full = nvalid == kR;
             double acc[kR];
 #pragma unroll
             for (int r = 0; r < kR; r++) acc[r] = 0.0;
             if (L > 0) {
-                synthesis_item<(L > 0 ? L : 2), kR>(cur, base, d, in_ext - 1, a.f.h, acc);
-                if (have_w) synthesis_item<(L > 0 ? L : 2), kR>(wt, base, d, in_ext - 1, a.f.g, acc);
+                constexpr int LL = L > 0 ? L : 2;
+                if (full) {
+                    synthesis_item<LL, kR, true>(cur + base, d, nvalid, a.f.h, acc);
+                    if (have_w) synthesis_item<LL, kR, true>(wt + base, d, nvalid, a.f.g, acc);
+                } else {
+                    synthesis_item<LL, kR, false>(cur + base, d, nvalid, a.f.h, acc);
+                    if (have_w) synthesis_item<LL, kR, false>(wt + base, d, nvalid, a.f.g, acc);
+                }
             } else {
                 synthesis_item_dyn<kR>(cur, base, d, in_ext - 1, LR, a.f.h, acc);
                 if (have_w) synthesis_item_dyn<kR>(wt, base, d, in_ext - 1, LR, a.f.g, acc);
             }
+            double *q = nxt + base;
 #pragma unroll
-            for (int r = 0; r < kR; r++) {
-                const int i = base + (r << ld2);
-                if (i < M) nxt[i] = acc[r];
-            }
+            for (int r = 0; r < kR; r++) { if (full || r < nvalid) *q = acc[r]; q += d; }
         }
         fence_async_smem();   // order this level's generic-proxy traffic before later bulk copies touch the buffers
         __syncthreads();
@@ -471,6 +505,111 @@ int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
 
 }  // namespace
 
+namespace {
+
+int64_t even_up(int64_t v) { return (v + 1) & ~1ll; }
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
+    if (fwd) return (size_t)((2 * (tile + htot) + (use_stage ? 2 * tile : 0)) * 8 + 64);
+    return (size_t)(4 * (tile + htot) * 8 + 64);
+}
+
+// modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
+double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t t) {
+    const int64_t d0 = 1ll << (first - 1);
+    const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
+    const int64_t htot = even_up(hexact);
+    const bool use_stage = fwd && d0 < 4;
+    const size_t smem = smem_bytes(fwd, t, htot, use_stage);
+    if (smem > ctx->smem_optin - 1024) return INFINITY;
+    const int regs = l <= 12 ? 85 : 128;
+    int64_t ctas = std::min<int64_t>((int64_t)(228 * 1024) / (int64_t)(smem + 1024), 65536 / (regs * kThreads));
+    ctas = std::min<int64_t>(ctas, 8);
+    if (ctas < 1) return INFINITY;
+    double dfma = 0.0, bytes = 0.0;
+    int64_t hsum = 0;
+    for (int i = 0; i < nf; i++) {
+        const int64_t d = d0 << i, H = (int64_t)(l - 1) * d;
+        hsum += H;
+        if (fwd) {
+            const int64_t hrem = i + 1 == nf ? 0 : hexact - hsum;  // halo region still needed by later levels
+            const int64_t items_h = hrem > 0 ? ceil_div(ceil_div(hrem, d), kR) * d : 0;
+            const int64_t items_o = ceil_div(ceil_div(t, d), kR) * d;
+            dfma += (double)(ceil_div(items_h, kThreads) * kThreads) * kR * l;
+            dfma += (double)(ceil_div(items_o, kThreads) * kThreads) * 2.0 * kR * l;
+        } else {
+            const int64_t m = t + (hsum - H);                       // outputs of level i: owned + halo of the levels below
+            const int64_t items = ceil_div(ceil_div(m, d), kR) * d;
+            dfma += (double)(ceil_div(items, kThreads) * kThreads) * 2.0 * kR * l;
+            bytes += 8.0 * (double)(t + hsum);                      // W_i tile with its halo
+        }
+    }
+    if (fwd) bytes = 8.0 * (double)(t + htot) + 8.0 * (double)t * (nf + 1);
+    else bytes += 8.0 * (double)(t + htot) + 8.0 * (double)t;
+    const double c = dfma / 64.0 / 0.80;          // FP64 pipe: 64 DFMA/clk/SM, ~80 % reachable
+    const double m = bytes / 22.5 / 0.85;         // HBM fair share per SM per clock at 6.55 TB/s, 1.965 GHz
+    const double fixed = 3000.0 + 700.0 * nf;     // load latency, barriers, drain: hidden only across resident CTAs
+    const double time = std::max(std::max(c, m), (c + m + fixed) / (double)ctas);
+    return time / (double)t;
+}
+
+double group_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t n, int64_t *best_tile) {
+    const int64_t d0 = 1ll << (first - 1);
+    const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
+    const int64_t htot = even_up(hexact);
+    *best_tile = -1;
+    if (l < 2 || l > VW_FUSED_MAX_L || hexact > n || htot > 24576 || first + nf - 1 > 30) return INFINITY;
+    double best = INFINITY;
+    const int64_t tmin = std::max<int64_t>(512, fwd ? even_up(htot) : 512);
+    const int64_t ncap = even_up(n);
+    if (ctx->opt_tile > 0) {
+        int64_t t = std::max<int64_t>(even_up(ctx->opt_tile), fwd ? htot : 2);
+        *best_tile = std::min(t, ncap);
+        return tile_cost(ctx, fwd, l, first, nf, *best_tile);
+    }
+    for (int64_t t = tmin; t <= 28672; t += 256) {
+        const int64_t tt = std::min(t, ncap);
+        const double c = tile_cost(ctx, fwd, l, first, nf, tt);
+        if (c == INFINITY) break;
+        if (c < best * 0.985) { best = c; *best_tile = tt; }
+        if (tt == ncap) break;
+    }
+    return best;
+}
+
+}  // namespace
+
+int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out) {
+    out.clear();
+    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : 4;
+    const double kGeneric = 60.0;  // per-level kernels: one thread per output through L1/L2
+    std::vector<double> best(levels + 1, INFINITY);
+    std::vector<VwPlanGroup> pick(levels + 1);
+    best[0] = 0.0;
+    for (int done = 0; done < levels; done++) {
+        if (best[done] == INFINITY) continue;
+        for (int nf = 1; nf <= cap && done + nf <= levels; nf++) {
+            int64_t tile;
+            double c = group_cost(ctx, forward, l, done + 1, nf, n, &tile);
+            if (nf == 1 && done >= 5 && ctx->opt_poly != 0) {
+                // deep single level (dilation >= 32): the column kernel streams 24 B/sample with no halo recompute
+                bool has = l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12 || l == 16 || l == 18 || l == 20 || l == 30;
+                const double ccol = std::max(2.0 * l / 64.0 / 0.70, 24.0 / 22.5 / 0.80) + 0.1;
+                if (has && ccol < c) { c = ccol; tile = -2; }
+            }
+            if (c == INFINITY) { if (nf > 1) continue; c = kGeneric; tile = -1; }
+            if (best[done] + c < best[done + nf]) {
+                best[done + nf] = best[done] + c;
+                pick[done + nf] = VwPlanGroup{done + 1, nf, tile, c};
+            }
+        }
+    }
+    for (int at = levels; at > 0; at -= pick[at].nlev) out.push_back(pick[at]);
+    std::reverse(out.begin(), out.end());   // ascending levels; the inverse walks it backwards
+    return VW_OK;
+}
+
 int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     if (p.l < 2 || p.l > VW_FUSED_MAX_L || p.nlevels < 1 || p.batch < 1 || p.n_out < 1) return VW_EUNSUPPORTED;
     const int64_t d0 = 1ll << (p.first_level - 1);
@@ -481,19 +620,17 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     const bool use_stage = d0 < 4;
     const bool use_tma = aligned16(p.x) && aligned16(p.w) && aligned16(p.v) && !(p.ldx & 1) && !(p.ldw & 1) &&
                          !(p.lsw & 1) && !(p.ldv & 1) && !(p.n_in & 1) && !(p.t0 & 1) && !(p.n_out & 1);
-    // tile: as many owned samples as keep every level of the group within one item per thread, within smem
     const size_t smem_cap = ctx->smem_optin - 1024;
-    int64_t tile = ctx->opt_tile > 0 ? ctx->opt_tile : (int64_t)kR * kThreads - (htot - (int64_t)(p.l - 1) * d0);
-    if (tile < htot) tile = htot;            // the symmetric mirror patch needs the sources inside the tile
-    if (tile < 512) tile = 512;
-    auto smem_for = [&](int64_t t) { return (size_t)((2 * (t + htot) + (use_stage ? 2 * t : 0)) * 8 + 64); };
-    while (smem_for(tile) > smem_cap && tile > 512) tile -= 256;
-    if (smem_for(tile) > smem_cap || tile < htot) return VW_EUNSUPPORTED;
-    tile &= ~1ll;
+    int64_t tile = p.tile;
+    if (tile <= 0 && group_cost(ctx, true, p.l, p.first_level, p.nlevels, p.n_out, &tile) == INFINITY) return VW_EUNSUPPORTED;
+    if (tile < htot) tile = htot;            // the symmetric mirror patch needs its sources inside the tile
+    tile = even_up(tile);
+    auto smem_for = [&](int64_t t) { return smem_bytes(true, t, htot, use_stage); };
+    if (smem_for(tile) > smem_cap) return VW_EUNSUPPORTED;
     if (ctx->opt_tile <= 0) {  // equal tiles: ceil(n_out / ntiles), even
         int64_t nt = (p.n_out + tile - 1) / tile;
         int64_t bal = (((p.n_out + nt - 1) / nt) + 1) & ~1ll;
-        if (bal >= htot || p.mode != VW_SYMMETRIC) tile = bal;
+        if (bal >= htot) tile = bal;
     }
     if (tile > p.n_out) tile = (p.n_out + 1) & ~1ll;
     if (p.mode == VW_SYMMETRIC && (p.n_in < htot || tile < htot)) return VW_EUNSUPPORTED;
@@ -532,12 +669,11 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     const bool use_tma = (!p.v || aligned16(p.v)) && aligned16(p.w) && aligned16(p.out) && !(p.ldv & 1) && !(p.ldw & 1) &&
                          !(p.lsw & 1) && !(p.ldo & 1) && !(p.n_in & 1) && !(p.n_out & 1);
     const size_t smem_cap = ctx->smem_optin - 1024;
-    int64_t tile = ctx->opt_tile > 0 ? ctx->opt_tile : (int64_t)kR * kThreads - htot;
-    if (tile < 512) tile = 512;
-    auto smem_for = [&](int64_t t) { return (size_t)(4 * (t + htot) * 8 + 64); };
-    while (smem_for(tile) > smem_cap && tile > 512) tile -= 256;
+    int64_t tile = p.tile;
+    if (tile <= 0 && group_cost(ctx, false, p.l, p.first_level, p.nlevels, p.n_out, &tile) == INFINITY) return VW_EUNSUPPORTED;
+    tile = even_up(tile);
+    auto smem_for = [&](int64_t t) { return smem_bytes(false, t, htot, false); };
     if (smem_for(tile) > smem_cap) return VW_EUNSUPPORTED;
-    tile &= ~1ll;
     if (ctx->opt_tile <= 0) {
         int64_t nt = (p.n_out + tile - 1) / tile;
         tile = (((p.n_out + nt - 1) / nt) + 1) & ~1ll;

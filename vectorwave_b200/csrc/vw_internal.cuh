@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "vw_modwt.h"
 
@@ -68,6 +69,7 @@ struct VwFusedFwd {
     double *v; int64_t ldv;                  // V_{first+nlev-1}
     int64_t batch, n_in, t0, n_out;          // outputs cover input positions [t0, t0+n_out)
     int l, first_level, nlevels, mode;
+    int64_t tile;                            // 0 = choose here
 };
 int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f);
 struct VwFusedInv {
@@ -78,8 +80,23 @@ struct VwFusedInv {
     int64_t batch, n_in, n_out;              // outputs cover positions [0, n_out) of the input buffers
     int l, first_level, nlevels, mode;
     const double *thr_dev; int thr_per_row; int thr_soft;  // optional fused thresholding of W on load
+    int64_t tile;                            // 0 = choose here
 };
+
+// Level schedule: which consecutive levels share one fused launch and with which tile, from a small cost model
+// (FP64-pipe cycles incl. halo recompute and ragged rounds vs HBM bytes incl. halo re-reads, overlapped across the
+// CTAs that fit one SM).  tile < 0 marks a level that only the per-level kernels can take.
+struct VwPlanGroup { int first, nlev; int64_t tile; double cost; };
+#include <vector>
+int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out);
 int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f);
+
+// ---- deep single levels, dilation >= 32 (vw_column.cu): register sliding window per dilation column ---------
+int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int64_t ldv, double *w, int64_t ldw,
+                       int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode);
+int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double *w, int64_t ldw, double *out, int64_t ldo,
+                        int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode,
+                        vw_align al);
 
 // ---- exact order statistics (vw_select.cu) ---------------------------------------------------
 // median(|w1|) per row -> universal thresholds written to thr_dev[batch] (device).

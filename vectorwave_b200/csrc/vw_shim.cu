@@ -138,70 +138,65 @@ int finish(vw_ctx *ctx, uint32_t flags, bool host_io) {
 // device-resident cores.  All pointers are device pointers here.
 // ------------------------------------------------------------------------------------------------
 
-// How many levels (>= 1) starting at `first` may share one fused launch, given the smem budget.
-int fuse_depth(const vw_ctx *ctx, int l, int first, int remaining, int64_t n) {
-    int cap = ctx->opt_fuse > 0 ? (int)ctx->opt_fuse : 4;
-    int f = std::min(cap, remaining);
-    // keep the fused halo (l-1)*2^(first-1)*(2^f-1) well below both the tile and the signal
-    while (f > 1) {
-        long double halo = (long double)(l - 1) * (long double)((int64_t)1 << (first - 1)) * (long double)(((int64_t)1 << f) - 1);
-        if (halo <= 2048.0L && halo <= (long double)n) break;
-        f--;
-    }
-    return f;
-}
+vw_align default_align() { return vw_align{1, 0, 1, 0}; }
 
+// Analysis cascade over device buffers.  Groups of levels come from the planner; a group the fused kernel declines
+// (unaligned rows, exotic filter length, ...) runs level by level on the generic kernels.
 int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const VwFilt &f, int l,
                    int levels, int mode, double *w, int64_t ldw, int64_t lsw, double *vj, int64_t ldv, uint32_t flags) {
     const bool exact = flags & VW_FLAG_BITEXACT;
     const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE);
-    // ping-pong approximations in scratch; the last level writes straight to vj
+    std::vector<VwPlanGroup> plan;
+    if (allow_fused) vw_plan_levels(ctx, true, l, levels, n, plan);
+    else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
     double *buf[2] = {nullptr, nullptr};
     const double *cur = x;
     int64_t ld_cur = ldx;
-    int level = 1, pp = 0;
-    while (level <= levels) {
-        int rc;
-        // destination of the approximation leaving a group that ends at level `end`
-        auto pick_out = [&](int end, double *&vout, int64_t &ld_vout) -> int {
-            if (end == levels) { vout = vj; ld_vout = ldv; return VW_OK; }
-            if (!buf[pp]) {
-                void *p;
-                int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
-                if (r) return r;
-                buf[pp] = (double *)p;
-            }
-            vout = buf[pp];
-            ld_vout = n;
-            return VW_OK;
-        };
-        int nf = allow_fused ? fuse_depth(ctx, l, level, levels - level + 1, n) : 1;
+    int pp = 0;
+    // destination of the approximation leaving level `end`: the caller's V_J for the last level, else ping-pong scratch
+    auto pick_out = [&](int end, double *&vout, int64_t &ld_vout) -> int {
+        if (end == levels) { vout = vj; ld_vout = ldv; return VW_OK; }
+        if (!buf[pp]) {
+            void *p;
+            int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
+            if (r) return r;
+            buf[pp] = (double *)p;
+        }
+        vout = buf[pp];
+        ld_vout = n;
+        return VW_OK;
+    };
+    for (const VwPlanGroup &g : plan) {
+        int rc = VW_EUNSUPPORTED;
         double *vout = nullptr;
         int64_t ld_vout = 0;
-        rc = VW_EUNSUPPORTED;
-        if (allow_fused) {
-            if ((rc = pick_out(level + nf - 1, vout, ld_vout))) return rc;
-            VwFusedFwd p{cur, ld_cur, w + (int64_t)(level - 1) * lsw, ldw, lsw, vout, ld_vout, batch, n, 0, n,
-                         l, level, nf, mode};
+        if (allow_fused && g.tile > 0) {
+            if ((rc = pick_out(g.first + g.nlev - 1, vout, ld_vout))) return rc;
+            VwFusedFwd p{cur, ld_cur, w + (int64_t)(g.first - 1) * lsw, ldw, lsw, vout, ld_vout, batch, n, 0, n,
+                         l, g.first, g.nlev, mode, g.tile};
             rc = vw_fused_forward(ctx, p, f);
             if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            if (rc == VW_OK) { cur = vout; ld_cur = ld_vout; pp ^= 1; }
         }
         if (rc == VW_EUNSUPPORTED) {
-            nf = 1;
-            if ((rc = pick_out(level, vout, ld_vout))) return rc;
-            rc = vw_launch_analysis_level(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n, 0, n,
-                                          batch, f, l, (int64_t)1 << (level - 1), mode, exact);
-            if (rc) return rc;
+            for (int level = g.first; level < g.first + g.nlev; level++) {
+                if ((rc = pick_out(level, vout, ld_vout))) return rc;
+                rc = VW_EUNSUPPORTED;
+                if (allow_fused && level >= 6 && ctx->opt_poly != 0) {
+                    rc = vw_column_analysis(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n, 0, n,
+                                            batch, f, l, (int64_t)1 << (level - 1), mode);
+                    if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+                }
+                if (rc == VW_EUNSUPPORTED)
+                    rc = vw_launch_analysis_level(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n,
+                                                  0, n, batch, f, l, (int64_t)1 << (level - 1), mode, exact);
+                if (rc) return rc;
+                cur = vout; ld_cur = ld_vout; pp ^= 1;
+            }
         }
-        cur = vout;
-        ld_cur = ld_vout;
-        pp ^= 1;
-        level += nf;
     }
     return VW_OK;
 }
-
-vw_align default_align() { return vw_align{1, 0, 1, 0}; }
 
 int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const double *vj, int64_t ldv,
                    int64_t batch, int64_t n, const VwFilt &f, int l, int levels, int mode, const vw_align *align,
@@ -214,62 +209,58 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
         for (int j = 0; j < levels; j++)
             plain = plain && align[j].sigma_h == 1 && align[j].sigma_g == 1 && align[j].tau_h == 0 && align[j].tau_g == 0;
     const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE) && plain && mode != VW_SYMMETRIC;
+    std::vector<VwPlanGroup> plan;
+    if (allow_fused) vw_plan_levels(ctx, false, l, levels, n, plan);
+    else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
     double *buf[2] = {nullptr, nullptr};
     const double *cur = use_approx ? vj : nullptr;
     int64_t ld_cur = ldv;
-    int level = levels, pp = 0;
-    while (level >= 1) {
-        int rc;
-        // group = levels [first, level], descending
-        int nf = 1;
-        if (allow_fused) {
-            int cap = ctx->opt_fuse > 0 ? (int)ctx->opt_fuse : 4;
-            nf = std::min(cap, level);
-            while (nf > 1) {
-                int first = level - nf + 1;
-                long double halo = (long double)(l - 1) * (long double)((int64_t)1 << (first - 1)) * (long double)(((int64_t)1 << nf) - 1);
-                if (halo <= 2048.0L && halo <= (long double)n) break;
-                nf--;
-            }
+    int pp = 0;
+    auto pick_out = [&](int first, double *&out, int64_t &ld_out) -> int {
+        if (first == 1) { out = xout; ld_out = ldx; return VW_OK; }
+        if (!buf[pp]) {
+            void *p;
+            int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
+            if (r) return r;
+            buf[pp] = (double *)p;
         }
-        auto pick_out = [&](int first, double *&out, int64_t &ld_out) -> int {
-            if (first == 1) { out = xout; ld_out = ldx; return VW_OK; }
-            if (!buf[pp]) {
-                void *p;
-                int r = vw_scratch(ctx, pp, (size_t)batch * (size_t)n * 8, &p);
-                if (r) return r;
-                buf[pp] = (double *)p;
-            }
-            out = buf[pp];
-            ld_out = n;
-            return VW_OK;
-        };
+        out = buf[pp];
+        ld_out = n;
+        return VW_OK;
+    };
+    for (int gi = (int)plan.size() - 1; gi >= 0; gi--) {
+        const VwPlanGroup &g = plan[gi];
+        int rc = VW_EUNSUPPORTED;
         double *out = nullptr;
         int64_t ld_out = 0;
-        rc = VW_EUNSUPPORTED;
-        if (allow_fused) {
-            int first = level - nf + 1;
-            if ((rc = pick_out(first, out, ld_out))) return rc;
-            VwFusedInv p{cur, ld_cur, w + (int64_t)(first - 1) * lsw, ldw, lsw,
-                         (detail_mask >> (first - 1)) & ((nf >= 64 ? ~0ull : ((1ull << nf) - 1))),
-                         out, ld_out, batch, n, n, l, first, nf, mode, thr_dev, thr_per_row, thr_soft};
+        if (allow_fused && g.tile > 0) {
+            if ((rc = pick_out(g.first, out, ld_out))) return rc;
+            VwFusedInv p{cur, ld_cur, w + (int64_t)(g.first - 1) * lsw, ldw, lsw,
+                         (detail_mask >> (g.first - 1)) & ((g.nlev >= 64 ? ~0ull : ((1ull << g.nlev) - 1))),
+                         out, ld_out, batch, n, n, l, g.first, g.nlev, mode, thr_dev, thr_per_row, thr_soft, g.tile};
             rc = vw_fused_inverse(ctx, p, f);
             if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            if (rc == VW_OK) { cur = out; ld_cur = ld_out; pp ^= 1; }
         }
         if (rc == VW_EUNSUPPORTED) {
-            nf = 1;
-            if ((rc = pick_out(level, out, ld_out))) return rc;
-            vw_align al = align ? align[level - 1] : default_align();
-            const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
-            if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
-            rc = vw_launch_synthesis_level(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
-                                           (int64_t)1 << (level - 1), mode, al, order == VW_ORDER_PAIR, exact);
-            if (rc) return rc;
+            for (int level = g.first + g.nlev - 1; level >= g.first; level--) {
+                if ((rc = pick_out(level, out, ld_out))) return rc;
+                vw_align al = align ? align[level - 1] : default_align();
+                const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
+                if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
+                rc = VW_EUNSUPPORTED;
+                if (!exact && !(flags & VW_FLAG_NO_FUSE) && level >= 6 && ctx->opt_poly != 0) {
+                    rc = vw_column_synthesis(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
+                                             (int64_t)1 << (level - 1), mode, al);
+                    if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+                }
+                if (rc == VW_EUNSUPPORTED)
+                    rc = vw_launch_synthesis_level(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
+                                                   (int64_t)1 << (level - 1), mode, al, order == VW_ORDER_PAIR, exact);
+                if (rc) return rc;
+                cur = out; ld_cur = ld_out; pp ^= 1;
+            }
         }
-        cur = out;
-        ld_cur = ld_out;
-        pp ^= 1;
-        level -= nf;
     }
     return VW_OK;
 }
@@ -375,6 +366,28 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
 }
 
 int64_t vw_launch_count(const vw_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int vw_describe_plan(int forward, int32_t l, int32_t levels, int64_t n, int64_t tile, int32_t fuse, char *out, size_t cap) {
+    if (!out || cap == 0) return -VW_ENULL;
+    if (l < 1 || levels < 1 || levels > VW_MAX_LEVELS || n < 1) return -VW_EINVAL;
+    vw_ctx fake;
+    fake.smem_optin = 227 * 1024;
+    fake.sm_count = 148;
+    fake.opt_tile = tile;
+    fake.opt_fuse = fuse;
+    std::vector<VwPlanGroup> plan;
+    vw_plan_levels(&fake, forward != 0, l, levels, n, plan);
+    size_t used = 0;
+    out[0] = 0;
+    for (const VwPlanGroup &g : plan) {
+        int k = snprintf(out + used, cap - used, "levels %d-%d: %s tile=%lld halo=%lld cost=%.2f cyc/sample/SM\n", g.first,
+                         g.first + g.nlev - 1, g.tile > 0 ? "fused" : (g.tile == -2 ? "column" : "per-level"), (long long)g.tile,
+                         (long long)((int64_t)(l - 1) * ((int64_t)1 << (g.first - 1)) * (((int64_t)1 << g.nlev) - 1)), g.cost);
+        if (k < 0 || (size_t)k >= cap - used) break;
+        used += (size_t)k;
+    }
+    return (int)plan.size();
+}
 
 void *vw_alloc_pinned(size_t bytes) {
     void *p = nullptr;
@@ -684,7 +697,7 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
     rc = VW_EUNSUPPORTED;
     if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
         VwFusedFwd p{vin, n_in, w, n_local, level_stride_w, vout, n_local, 1, n_in, halo, n_local,
-                     l, first_level, nlevels, VW_MODE_LINEAR};
+                     l, first_level, nlevels, VW_MODE_LINEAR, 0};
         rc = vw_fused_forward(ctx, p, f);
         if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
     }
@@ -746,7 +759,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
     rc = VW_EUNSUPPORTED;
     if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
         VwFusedInv p{vin, n_in, w, n_in, level_stride_w, nlevels >= 64 ? ~0ull : ((1ull << nlevels) - 1), vout, n_local,
-                     1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0};
+                     1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0, 0};
         rc = vw_fused_inverse(ctx, p, f);
         if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
     }
