@@ -66,6 +66,8 @@ if __name__ == "__main__":
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--fuse", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--poly", type=int, default=1)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse}, a.mode)
+        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly}, a.mode)

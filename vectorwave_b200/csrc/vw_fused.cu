@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int kR = 9;          // outputs per thread item (odd => conflict-free strided LDS.64)
-constexpr int kThreads = 256;  // threads per CTA
+constexpr int kThreads = 256;  // maximum threads per CTA (launch bound); the launch may use fewer
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copies (TMA)
@@ -86,12 +86,12 @@ __device__ __forceinline__ void stage_tile(double *dst, const double *__restrict
                                            int mode, bool use_tma, uint64_t *bar, bool row_is_null) {
     const int tid = threadIdx.x;
     if (row_is_null) {
-        for (int i = tid; i < count; i += kThreads) dst[i] = 0.0;
+        for (int i = tid; i < count; i += (int)blockDim.x) dst[i] = 0.0;
         if (use_tma && tid == 0) mbar_expect_tx(bar, 0);
         return;
     }
     if (!use_tma) {
-        for (int i = tid; i < count; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
+        for (int i = tid; i < count; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
         return;
     }
     if (mode == VW_PERIODIC) {
@@ -117,8 +117,8 @@ __device__ __forceinline__ void stage_tile(double *dst, const double *__restrict
         mbar_expect_tx(bar, (uint32_t)(b - a) * 8u);
         if (b > a) bulk_g2s(dst + a, row + lo, (uint32_t)(b - a) * 8u, bar);
     }
-    for (int i = tid; i < a; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
-    for (int i = b + tid; i < count; i += kThreads) dst[i] = ext_load(row, pos0 + i, n, mode);
+    for (int i = tid; i < a; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
+    for (int i = b + tid; i < count; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
             if (M <= 0) continue;
             const int Q = (M + d - 1) >> ld2;                  // samples per phase (max)
             const int items = ((Q + kR - 1) / kR) << ld2;      // chunks x phases
-            for (int wi = tid; wi < items; wi += kThreads) {
+            for (int wi = tid; wi < items; wi += (int)blockDim.x) {
                 const int c = wi >> ld2, ph = wi & (d - 1);
                 const int base = ra + ((c * kR) << ld2) + ph;
                 if (base >= rb) continue;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         // SYMMETRIC: V_lev at positions < 0 is the mirror of V_lev itself (ScalarOps.java:818-835 applied per level)
         if (a.mode == VW_SYMMETRIC && !last && g0 - HT < 0) {
             const int neg = (int)(HT - g0);                     // tile indices [0, neg) are positions < 0
-            for (int i = lo_cur + tid; i < neg; i += kThreads) {
+            for (int i = lo_cur + tid; i < neg; i += (int)blockDim.x) {
                 const long long pos = g0 - HT + i;              // negative
                 nxt[i] = nxt[(int)((-1 - pos) - (g0 - HT))];
             }
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                     bulk_wait_read<1>();  // the other staging buffer is free again before anyone writes it
                 }
             } else {
-                for (int i = tid; i < Tt; i += kThreads) wrow[i] = stg[i];
+                for (int i = tid; i < Tt; i += (int)blockDim.x) wrow[i] = stg[i];
             }
             __syncthreads();
         }
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
             bulk_wait_read<0>();
         }
     } else {
-        for (int i = tid; i < Tt; i += kThreads) vrow[i] = cur[HT + i];
+        for (int i = tid; i < Tt; i += (int)blockDim.x) vrow[i] = cur[HT + i];
     }
     (void)pending_stage;
 }
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         if (a.thr && have_w) {
             // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118)
             const double lam = a.thr[a.thr_per_row ? b : 0];
-            for (int i = tid; i < in_ext; i += kThreads) {
+            for (int i = tid; i < in_ext; i += (int)blockDim.x) {
                 const double c = wt[i], ab = fabs(c), m = ab - lam;
                 double r;
                 if (a.thr_soft) r = ab > lam ? (c > 0.0 ? m : (c < 0.0 ? -m : c * m)) : 0.0;
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         const int M = lev > 0 ? extent(lev - 1) : Tt;           // outputs of this level
         const int Q = (M + d - 1) >> ld2;
         const int items = ((Q + kR - 1) / kR) << ld2;
-        for (int wi = tid; wi < items; wi += kThreads) {
+        for (int wi = tid; wi < items; wi += (int)blockDim.x) {
             const int c = wi >> ld2, ph = wi & (d - 1);
             const int base = ((c * kR) << ld2) + ph;
             if (base >= M) continue;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
             bulk_wait_read<0>();
         }
     } else {
-        for (int i = tid; i < Tt; i += kThreads) orow[i] = cur[i];
+        for (int i = tid; i < Tt; i += (int)blockDim.x) orow[i] = cur[i];
     }
 }
 
@@ -517,6 +517,7 @@ size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
 double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t t) {
+    const int nthreads = ctx->opt_threads > 0 ? (int)ctx->opt_threads : kThreads;
     const int64_t d0 = 1ll << (first - 1);
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
@@ -524,7 +525,7 @@ double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t 
     const size_t smem = smem_bytes(fwd, t, htot, use_stage);
     if (smem > ctx->smem_optin - 1024) return INFINITY;
     const int regs = l <= 12 ? 85 : 128;
-    int64_t ctas = std::min<int64_t>((int64_t)(228 * 1024) / (int64_t)(smem + 1024), 65536 / (regs * kThreads));
+    int64_t ctas = std::min<int64_t>((int64_t)(228 * 1024) / (int64_t)(smem + 1024), 65536 / (regs * nthreads));
     ctas = std::min<int64_t>(ctas, 8);
     if (ctas < 1) return INFINITY;
     double dfma = 0.0, bytes = 0.0;
@@ -536,12 +537,12 @@ double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t 
             const int64_t hrem = i + 1 == nf ? 0 : hexact - hsum;  // halo region still needed by later levels
             const int64_t items_h = hrem > 0 ? ceil_div(ceil_div(hrem, d), kR) * d : 0;
             const int64_t items_o = ceil_div(ceil_div(t, d), kR) * d;
-            dfma += (double)(ceil_div(items_h, kThreads) * kThreads) * kR * l;
-            dfma += (double)(ceil_div(items_o, kThreads) * kThreads) * 2.0 * kR * l;
+            dfma += (double)(ceil_div(items_h, nthreads) * nthreads) * kR * l;
+            dfma += (double)(ceil_div(items_o, nthreads) * nthreads) * 2.0 * kR * l;
         } else {
             const int64_t m = t + (hsum - H);                       // outputs of level i: owned + halo of the levels below
             const int64_t items = ceil_div(ceil_div(m, d), kR) * d;
-            dfma += (double)(ceil_div(items, kThreads) * kThreads) * 2.0 * kR * l;
+            dfma += (double)(ceil_div(items, nthreads) * nthreads) * 2.0 * kR * l;
             bytes += 8.0 * (double)(t + hsum);                      // W_i tile with its halo
         }
     }
@@ -646,11 +647,12 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
+    const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
     int rc = VW_OK;
 #define VW_FWD_CALL(LL)                                                                    \
     do {                                                                                   \
         if ((rc = set_smem(ctx, k_fused_analysis<LL>, smem))) return rc;                   \
-        k_fused_analysis<LL><<<grid, kThreads, smem, ctx->stream>>>(a);                    \
+        k_fused_analysis<LL><<<grid, nthreads, smem, ctx->stream>>>(a);                    \
     } while (0)
     VW_DISPATCH_L(p.l, VW_FWD_CALL)
 #undef VW_FWD_CALL
@@ -691,11 +693,12 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
+    const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
     int rc = VW_OK;
 #define VW_INV_CALL(LL)                                                                    \
     do {                                                                                   \
         if ((rc = set_smem(ctx, k_fused_synthesis<LL>, smem))) return rc;                  \
-        k_fused_synthesis<LL><<<grid, kThreads, smem, ctx->stream>>>(a);                   \
+        k_fused_synthesis<LL><<<grid, nthreads, smem, ctx->stream>>>(a);                   \
     } while (0)
     VW_DISPATCH_L(p.l, VW_INV_CALL)
 #undef VW_INV_CALL
