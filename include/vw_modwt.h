@@ -121,6 +121,9 @@ VW_API int vw_set_option(vw_ctx *ctx, const char *name, int64_t value);
  * forward != 0: analysis; else synthesis.  Returns the number of launch groups, or a negative vw_status. */
 VW_API int vw_describe_plan(int forward, int32_t l, int32_t levels, int64_t n, int64_t tile, int32_t fuse, char *out,
                             size_t cap);
+/* The same schedule as numbers: group g covers levels first[g] .. first[g]+nlev[g]-1.  Returns the group count
+ * (<= cap) or a negative vw_status.  Used by the span-sharded host code to align halo exchanges with launches. */
+VW_API int vw_plan_query(int forward, int32_t l, int32_t levels, int64_t n, int32_t *first, int32_t *nlev, int32_t cap);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 VW_API int64_t vw_launch_count(const vw_ctx *ctx);
 

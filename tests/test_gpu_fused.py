@@ -246,3 +246,22 @@ def test_deep_levels_column_kernels(eng, mode, name, n, levels):
     # the column kernels must agree with the per-level kernels they replace
     w2, v2 = eng.forward(x, h * S, g * S, levels, mode, _native.FLAG_NO_FUSE)
     np.testing.assert_allclose(w, w2, rtol=0, atol=1e-13)
+
+
+def test_span_sharded_class_single_rank_on_device(eng):
+    """SpanShardedMODWT with the real engine, world = 1 (the ring wraps onto itself): equals the oracle."""
+    import torch
+    from vectorwave_b200.sharded import SpanShardedMODWT
+    rng = np.random.default_rng(33)
+    n = 1 << 16
+    x = rng.standard_normal(n)
+    for name, levels, mode in (("sym8", 7, vw.BoundaryMode.PERIODIC), ("db4", 6, vw.BoundaryMode.ZERO_PADDING),
+                               ("coif5", 8, vw.BoundaryMode.PERIODIC)):
+        h, g, wid = filters(name)
+        sh = SpanShardedMODWT(vw.get_wavelet(name), levels, n, mode, engine=eng, rank=0, world=1)
+        res = sh.forward(torch.as_tensor(x, device="cuda"))
+        wo, vo = cref.decompose(x, h, g, levels, mode.value)
+        np.testing.assert_allclose(res.details().cpu().numpy(), wo, rtol=0, atol=tol(x))
+        np.testing.assert_allclose(res.approximation().cpu().numpy(), vo, rtol=0, atol=tol(x))
+        xr = sh.inverse(res, order=1 if mode == vw.BoundaryMode.ZERO_PADDING else 0)
+        np.testing.assert_allclose(xr.cpu().numpy(), cref.reconstruct(wo, vo, h, g, mode.value, wid), rtol=0, atol=tol(x))

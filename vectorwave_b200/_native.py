@@ -60,6 +60,7 @@ SIGNATURES = {
     "vw_device_index": (C.c_int, [_vp]),
     "vw_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "vw_launch_count": (_i64, [_vp]),
+    "vw_plan_query": (C.c_int, [C.c_int, _i32, _i32, _i64, C.POINTER(_i32), C.POINTER(_i32), _i32]),
     "vw_describe_plan": (C.c_int, [C.c_int, _i32, _i32, _i64, _i64, _i32, C.c_char_p, C.c_size_t]),
     "vw_alloc_pinned": (_vp, [C.c_size_t]),
     "vw_free_pinned": (None, [_vp]),
@@ -112,6 +113,16 @@ def describe_plan(forward, l, levels, n, tile=0, fuse=0):
     if rc < 0:
         raise IllegalArgumentException(f"vw_describe_plan failed: {rc}")
     return buf.value.decode()
+
+
+def plan_groups(forward, l, levels, n):
+    """[(first_level, nlevels), ...] of the engine's launch schedule (host logic only)."""
+    first = (_i32 * 64)()
+    nlev = (_i32 * 64)()
+    rc = load_library().vw_plan_query(int(bool(forward)), int(l), int(levels), int(n), first, nlev, 64)
+    if rc < 0:
+        raise IllegalArgumentException(f"vw_plan_query failed: {rc}")
+    return [(int(first[i]), int(nlev[i])) for i in range(rc)]
 
 
 def _is_torch(x):
@@ -393,13 +404,15 @@ class Engine:
     def span_halo(self, l, first_level, nlevels):
         return int(self.lib.vw_span_halo(int(l), int(first_level), int(nlevels)))
 
-    def forward_span(self, vin_ext, halo, hs, gs, first_level, nlevels, flags=0):
-        """vin_ext: 1-D CUDA tensor [halo | span] -> (W [nlevels][n_local], V [n_local])."""
+    def forward_span(self, vin_ext, halo, hs, gs, first_level, nlevels, flags=0, w_out=None, v_out=None):
+        """vin_ext: 1-D CUDA tensor [halo | span] -> (W [nlevels][n_local], V [n_local]).
+        w_out: optional [nlevels][>= n_local] rows (row stride free), v_out: optional [n_local] (may be a slice)."""
         import torch
         n_local = vin_ext.numel() - halo
         hs, gs = _fp(hs), _fp(gs)
-        w = torch.empty((nlevels, max(n_local, 1)), dtype=torch.float64, device=vin_ext.device)
-        v = torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
+        w = w_out if w_out is not None else torch.empty((nlevels, max(n_local, 1)), dtype=torch.float64,
+                                                        device=vin_ext.device)
+        v = v_out if v_out is not None else torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
         fl = self._bind_stream(vin_ext, w, v) | flags
         with self._call_lock:
             self._check(self.lib.vw_modwt_forward_span(
@@ -408,13 +421,14 @@ class Engine:
                 _vp(v.data_ptr()), fl))
         return w, v
 
-    def inverse_span(self, vin_ext, w_ext, halo, hs, gs, first_level, nlevels, order=ORDER_SPLIT, flags=0):
+    def inverse_span(self, vin_ext, w_ext, halo, hs, gs, first_level, nlevels, order=ORDER_SPLIT, flags=0, out=None):
         """vin_ext [span | halo], w_ext [nlevels][span | halo] (CUDA) -> V_{first-1} [n_local]."""
         import torch
         n_local = vin_ext.numel() - halo
         hs, gs = _fp(hs), _fp(gs)
-        w_ext = w_ext.contiguous()
-        out = torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
+        if w_ext.stride(1) != 1:
+            w_ext = w_ext.contiguous()
+        out = out if out is not None else torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
         fl = self._bind_stream(vin_ext, w_ext, out) | flags
         with self._call_lock:
             self._check(self.lib.vw_modwt_inverse_span(

@@ -367,6 +367,19 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
 
 int64_t vw_launch_count(const vw_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+int vw_plan_query(int forward, int32_t l, int32_t levels, int64_t n, int32_t *first, int32_t *nlev, int32_t cap) {
+    if (!first || !nlev) return -VW_ENULL;
+    if (l < 1 || levels < 1 || levels > VW_MAX_LEVELS || n < 1) return -VW_EINVAL;
+    vw_ctx fake;
+    fake.smem_optin = 227 * 1024;
+    fake.sm_count = 148;
+    std::vector<VwPlanGroup> plan;
+    vw_plan_levels(&fake, forward != 0, l, levels, n, plan);
+    if ((int)plan.size() > cap) return -VW_ELENGTH;
+    for (size_t i = 0; i < plan.size(); i++) { first[i] = plan[i].first; nlev[i] = plan[i].nlev; }
+    return (int)plan.size();
+}
+
 int vw_describe_plan(int forward, int32_t l, int32_t levels, int64_t n, int64_t tile, int32_t fuse, char *out, size_t cap) {
     if (!out || cap == 0) return -VW_ENULL;
     if (l < 1 || levels < 1 || levels > VW_MAX_LEVELS || n < 1) return -VW_EINVAL;
@@ -723,9 +736,15 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
             }
             // analysis over input coords: in = cur (position cur_off at index 0), outputs [start, n_in)
             // W rows only exist for the span: write them via a second launch restricted to [halo, n_in)
-            rc = vw_launch_analysis_level(ctx, cur, 0, last ? vout : vdst, 0, last ? w + (int64_t)i * level_stride_w : nullptr,
-                                          0, n_in - cur_off, (last ? halo : start) - cur_off, last ? n_local : n_in - start,
-                                          1, f, l, d, VW_MODE_LINEAR, exact);
+            rc = VW_EUNSUPPORTED;
+            if (last && nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= 32 && ctx->opt_poly != 0) {
+                rc = vw_column_analysis(ctx, cur, 0, vout, 0, w, 0, n_in, halo, n_local, 1, f, l, d, VW_MODE_LINEAR);
+                if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            }
+            if (rc == VW_EUNSUPPORTED)
+                rc = vw_launch_analysis_level(ctx, cur, 0, last ? vout : vdst, 0, last ? w + (int64_t)i * level_stride_w : nullptr,
+                                              0, n_in - cur_off, (last ? halo : start) - cur_off, last ? n_local : n_in - start,
+                                              1, f, l, d, VW_MODE_LINEAR, exact);
             if (rc) return rc;
             if (!last) {
                 rc = vw_launch_analysis_level(ctx, cur, 0, nullptr, 0, w + (int64_t)i * level_stride_w, 0, n_in - cur_off,
@@ -777,8 +796,14 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                 if ((rc = vw_scratch(ctx, i & 1, (size_t)n_in * 8, &p))) return rc;
                 dst = (double *)p;
             }
-            rc = vw_launch_synthesis_level(ctx, cur, 0, w + (int64_t)i * level_stride_w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d,
-                                           VW_MODE_LINEAR, default_align(), order == VW_ORDER_PAIR, exact);
+            rc = VW_EUNSUPPORTED;
+            if (nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= 32 && ctx->opt_poly != 0) {
+                rc = vw_column_synthesis(ctx, cur, 0, w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d, VW_MODE_LINEAR, default_align());
+                if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            }
+            if (rc == VW_EUNSUPPORTED)
+                rc = vw_launch_synthesis_level(ctx, cur, 0, w + (int64_t)i * level_stride_w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d,
+                                               VW_MODE_LINEAR, default_align(), order == VW_ORDER_PAIR, exact);
             if (rc) return rc;
             cur = dst;
         }
