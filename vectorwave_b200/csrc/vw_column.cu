@@ -15,9 +15,22 @@
 
 namespace {
 
-constexpr int kCR = 9;         // rows per register block (synthesis; analysis uses col_rows<L>)
-template <int L> struct col_rows { static constexpr int value = L >= 24 ? 7 : 9; };
+constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value
+template <int L> struct col_rows { static constexpr int value = L >= 24 ? 8 : 9; };       // analysis
+template <int L> struct col_rows_syn { static constexpr int value = L >= 24 ? 6 : (L >= 16 ? 8 : 9); };  // synthesis (L-1+R sums)
 constexpr int kCThreads = 128;
+
+// Tap delivery.  sm_100 ptxas never folds a constant-bank operand into DFMA: taps go through uniform registers, and
+// there are only 63 of them.  Up to 12 taps (24 doubles = 48 URs) that is free; from 16 taps on ptxas spills URs to
+// vector registers and refills them with R2UR between the DFMAs (measured: DFMA < 45 % of issued instructions for
+// coif5).  Long filters therefore keep (h[k], g[k]) pairs in shared memory and fetch one pair per tap step with a
+// broadcast LDS.128 (volatile, so the loads stay inside the loop instead of being hoisted into 120 live registers):
+// 1 LDS per 2R DFMAs.
+template <int L> struct col_smem_taps { static constexpr bool value = L >= 16; };          // analysis
+template <int L> struct col_smem_taps_syn { static constexpr bool value = L >= 12; };      // synthesis
+__device__ __forceinline__ void lds_tap_pair(uint32_t addr, double &h, double &g) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(h), "=d"(g) : "r"(addr));
+}
 
 __device__ __forceinline__ int64_t wrap_mod(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
 // EDGE == false: the caller has proven pos is inside [0, n) (interior chunks, the overwhelming majority)
@@ -41,69 +54,117 @@ struct ColArgs {
     VwFilt32 f;                              // synthesis: taps already reversed for sigma = -1 streams
 };
 
+// Issue-slot budget (measured with tools/dfma_probe.cu on B200): a DFMA occupies the FP64 pipe for 2 cycles but one issue
+// slot; ALU-pipe integer instructions (IADD3, ISETP, LEA, LOP3) cost TWO issue slots each, FMA-pipe ones (IMAD, IMAD.WIDE,
+// IMAD.MOV) one.  At 60 DFMAs per sample (coif5) every integer instruction in the row loop shows up in the run time, so
+// the loops below keep one 64-bit byte pointer per stream that is bumped once per block, reach row r through
+// `ptr + d * (8 r)` (a single IMAD.WIDE with a 32-bit d), and use unpredicated loads / stores whenever a whole block
+// is in range.
+__device__ __forceinline__ const double *row_ptr(const char *base, int d, int r) {
+    return reinterpret_cast<const double *>(base + (long long)d * (long long)(8 * r));
+}
+__device__ __forceinline__ double *row_ptr(char *base, int d, int r) {
+    return reinterpret_cast<double *>(base + (long long)d * (long long)(8 * r));
+}
+
 // ---- analysis ------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)) k_column_analysis(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysis(const __grid_constant__ ColArgs a) {
     constexpr int R = col_rows<L>::value;
+    constexpr bool ST = col_smem_taps<L>::value;
+    __shared__ double2 s_taps[ST ? L : 1];
+    if (ST) {
+        if (threadIdx.x < L) s_taps[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
+        __syncthreads();
+    }
+    const uint32_t taps_addr = (uint32_t)__cvta_generic_to_shared(s_taps);
     // flattened (chunk, column) index, column fastest: 32 | d keeps every warp inside one chunk => coalesced rows
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
-    const long long col = gid & (a.d - 1);   // phase phi in [0, d)
+    const int d = (int)a.d;                   // host guarantees d <= 2^30
+    const int col = (int)(gid & (a.d - 1));   // phase phi in [0, d)
     const long long chunk = gid / a.d;
     if (chunk >= a.chunks) return;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        const double *x = a.x + b * a.ldx;
-        double *vo = a.v + b * a.ldv, *wo = a.w + b * a.ldw;
         // rows of this column inside the output range: positions t0 + col + q*d < t0 + n_out
         const long long rows = (a.n_out - col + a.d - 1) / a.d;
-        long long q = chunk * a.rows_per_chunk;
-        const long long qend = q + a.rows_per_chunk < rows ? q + a.rows_per_chunk : rows;
-        if (q >= qend) continue;
-        long long p = a.t0 + col + q * a.d;                // input-coordinate position of the current row
+        const long long q0 = chunk * a.rows_per_chunk;
+        long long left64 = rows - q0;
+        if (left64 <= 0) continue;
+        int left = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);   // rows this thread still owes
+        const long long p = a.t0 + col + q0 * a.d;        // input-coordinate position of the chunk's first row
+        const double *x = a.x + b * a.ldx;
+        const char *xp = reinterpret_cast<const char *>(x + p);                      // current block, row 0
+        char *vp = reinterpret_cast<char *>(a.v + b * a.ldv + (p - a.t0));
+        char *wp = reinterpret_cast<char *>(a.w + b * a.ldw + (p - a.t0));
         // seq[0 .. L-2] = the L-1 rows before the block (oldest first), seq[L-1 + r] = the block's new rows
         double seq[L - 1 + R];
         if (p - (long long)(L - 1) * a.d >= 0) {
 #pragma unroll
-            for (int i = 0; i < L - 1; i++) seq[i] = ext_load<false>(x, p - (long long)(L - 1 - i) * a.d, a.n_in, a.mode);
+            for (int i = 0; i < L - 1; i++) seq[i] = __ldg(row_ptr(xp, d, -(L - 1 - i)));
         } else {
 #pragma unroll
             for (int i = 0; i < L - 1; i++) seq[i] = ext_load<true>(x, p - (long long)(L - 1 - i) * a.d, a.n_in, a.mode);
         }
-        // software pipeline: the next block's rows are in flight while this block's FMAs run
+        // software pipeline: the next block's rows are in flight while this block's FMAs run (output rows lie inside [0, n_in))
         double nxt[R];
+        if (left >= R) {
 #pragma unroll
-        for (int r = 0; r < R; r++) nxt[r] = (q + r < qend) ? __ldg(x + p + r * a.d) : 0.0;   // output rows lie inside [0, n_in)
-        for (; q < qend; q += R) {
+            for (int r = 0; r < R; r++) nxt[r] = __ldg(row_ptr(xp, d, r));
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) nxt[r] = r < left ? __ldg(row_ptr(xp, d, r)) : 0.0;
+        }
+        while (left > 0) {
 #pragma unroll
             for (int r = 0; r < R; r++) seq[L - 1 + r] = nxt[r];
-            {
-                const long long qn = q + R, pn = p + (long long)R * a.d;
+            if (left >= 2 * R) {
 #pragma unroll
-                for (int r = 0; r < R; r++) nxt[r] = (qn + r < qend) ? __ldg(x + pn + r * a.d) : 0.0;
+                for (int r = 0; r < R; r++) nxt[r] = __ldg(row_ptr(xp, d, R + r));
+            } else if (left > R) {
+#pragma unroll
+                for (int r = 0; r < R; r++) nxt[r] = R + r < left ? __ldg(row_ptr(xp, d, R + r)) : 0.0;
             }
             double ah[R], ag[R];
 #pragma unroll
             for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
-            // out[r] = sum_k f[k] seq[L-1+r-k]; walk seq downwards so every output meets its taps in ascending order
+            if (ST) {
+                // out[r] = sum_k f[k] seq[L-1+r-k], tap-outer: one broadcast LDS.128 feeds 2R DFMAs, taps ascending
 #pragma unroll
-            for (int m = R - 1; m >= -(L - 1); m--) {
-                const double xv = seq[L - 1 + m];
+                for (int k = 0; k < L; k++) {
+                    double hk, gk;
+                    lds_tap_pair(taps_addr + 16u * k, hk, gk);
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int k = r - m;
-                    if (k >= 0 && k < L) { ah[r] = fma(a.f.h[k], xv, ah[r]); ag[r] = fma(a.f.g[k], xv, ag[r]); }
+                    for (int r = 0; r < R; r++) {
+                        const double xv = seq[L - 1 + r - k];
+                        ah[r] = fma(hk, xv, ah[r]);
+                        ag[r] = fma(gk, xv, ag[r]);
+                    }
+                }
+            } else {
+                // walk seq downwards so every output meets its taps in ascending order; taps live in uniform registers
+#pragma unroll
+                for (int m = R - 1; m >= -(L - 1); m--) {
+                    const double xv = seq[L - 1 + m];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int k = r - m;
+                        if (k >= 0 && k < L) { ah[r] = fma(a.f.h[k], xv, ah[r]); ag[r] = fma(a.f.g[k], xv, ag[r]); }
+                    }
                 }
             }
+            if (left >= R) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (q + r < qend) {
-                    const long long o = p - a.t0 + r * a.d;
-                    vo[o] = ah[r];
-                    wo[o] = ag[r];
-                }
+                for (int r = 0; r < R; r++) { *row_ptr(vp, d, r) = ah[r]; *row_ptr(wp, d, r) = ag[r]; }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (r < left) { *row_ptr(vp, d, r) = ah[r]; *row_ptr(wp, d, r) = ag[r]; }
             }
 #pragma unroll
             for (int i = 0; i < L - 1; i++) seq[i] = seq[i + R];   // slide: keep the last L-1 rows
-            p += (long long)R * a.d;
+            const long long step = (long long)d * (8 * R);
+            xp += step; vp += step; wp += step;
+            left -= R;
         }
     }
 }
@@ -113,79 +174,126 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)
 // with (taps, off) = (f, -tau) for sigma=+1 and (reversed f, tau - (L-1) d) for sigma=-1.
 // Transposed FIR: the thread keeps the L-1 unfinished output sums instead of two L-1 deep input windows (half the
 // registers): input row m adds th[k] V_m + tg[k] W_m to output m-k; an output is complete after input row o+L-1.
+// A chunk of `nout` output rows consumes nout + L-1 input rows; block i reads input rows [iR, iR+R) and completes
+// output rows [iR-(L-1), iR-(L-1)+R).
 template <int L, bool EDGE>
 __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *__restrict__ v, const double *__restrict__ w,
-                                                double *__restrict__ out, long long col, long long o_start, long long o_end,
-                                                long long pin) {
-    constexpr int R = col_rows<L>::value;
-    // acc[j] <-> output row  m0 - (L-1) + j ; rows below o_start are never emitted
+                                                char *op, int d, int nout, long long pin, uint32_t taps_addr) {
+    constexpr int R = col_rows_syn<L>::value;
+    // acc[j] <-> output row  m0 - (L-1) + j ; rows below 0 are never emitted
     double acc[L - 1 + R];
 #pragma unroll
     for (int j = 0; j < L - 1 + R; j++) acc[j] = 0.0;
-    const long long m_end = o_end + (L - 1);           // one past the last input row this chunk consumes
+    int in_left = nout + (L - 1);                 // input rows still to consume
+    int lead = L - 1;                             // output rows of the current block that precede the chunk (not emitted)
+    const char *vp = v ? reinterpret_cast<const char *>(v + pin + a.off_h) : nullptr;   // only dereferenced when !EDGE
+    const char *wp = w ? reinterpret_cast<const char *>(w + pin + a.off_g) : nullptr;
+    auto load_block = [&](int first, int avail, double (&nv)[R], double (&nw)[R]) {
+        // rows first .. first+R-1 relative to the current block start; `avail` = rows still in range counted from `first`
+        if (!EDGE && avail >= R) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                nv[r] = v ? __ldg(row_ptr(vp, d, first + r)) : 0.0;
+                nw[r] = w ? __ldg(row_ptr(wp, d, first + r)) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const bool live = r < avail;
+                if (EDGE) {
+                    const long long pos = pin + (long long)(first + r) * a.d;
+                    nv[r] = (live && v) ? ext_load<true>(v, pos + a.off_h, a.n_in, a.mode) : 0.0;
+                    nw[r] = (live && w) ? ext_load<true>(w, pos + a.off_g, a.n_in, a.mode) : 0.0;
+                } else {
+                    nv[r] = (live && v) ? __ldg(row_ptr(vp, d, first + r)) : 0.0;
+                    nw[r] = (live && w) ? __ldg(row_ptr(wp, d, first + r)) : 0.0;
+                }
+            }
+        }
+    };
     // software pipeline: block i+1's rows are in flight while block i's FMAs run
     double nv[R], nw[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const bool live = o_start + r < m_end;
-        const long long pos = pin + r * a.d;
-        nv[r] = (live && v) ? ext_load<EDGE>(v, pos + a.off_h, a.n_in, a.mode) : 0.0;
-        nw[r] = (live && w) ? ext_load<EDGE>(w, pos + a.off_g, a.n_in, a.mode) : 0.0;
-    }
-    for (long long m0 = o_start; m0 < m_end; m0 += R) {
+    load_block(0, in_left, nv, nw);
+    while (in_left > 0) {
         double cv[R], cw[R];
 #pragma unroll
         for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = nw[r]; }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const bool live = m0 + R + r < m_end;
-            const long long pos = pin + (long long)(R + r) * a.d;
-            nv[r] = (live && v) ? ext_load<EDGE>(v, pos + a.off_h, a.n_in, a.mode) : 0.0;
-            nw[r] = (live && w) ? ext_load<EDGE>(w, pos + a.off_g, a.n_in, a.mode) : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
+        if (in_left > R) load_block(R, in_left - R, nv, nw);
+        if (col_smem_taps_syn<L>::value) {
 #pragma unroll
             for (int k = 0; k < L; k++) {
-                const int j = r + L - 1 - k;
-                acc[j] = fma(a.f.h[k], cv[r], acc[j]);
-                acc[j] = fma(a.f.g[k], cw[r], acc[j]);
+                double hk, gk;
+                lds_tap_pair(taps_addr + 16u * k, hk, gk);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int j = r + L - 1 - k;
+                    acc[j] = fma(hk, cv[r], acc[j]);
+                    acc[j] = fma(gk, cw[r], acc[j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+                for (int k = 0; k < L; k++) {
+                    const int j = r + L - 1 - k;
+                    acc[j] = fma(a.f.h[k], cv[r], acc[j]);
+                    acc[j] = fma(a.f.g[k], cw[r], acc[j]);
+                }
             }
         }
-        // outputs j in [0, R) are complete: rows m0-(L-1) .. m0-(L-1)+R-1
+        // outputs j in [0, R) are complete: chunk rows  m0-(L-1)+j; op points at chunk row m0-(L-1) (may precede the chunk)
+        // (row j of the block is chunk row m0-(L-1)+j: inside the chunk iff lead <= j < in_left)
+        if (lead <= 0 && in_left >= R) {
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            const long long o = m0 - (L - 1) + j;
-            if (o >= o_start && o < o_end) out[col + o * a.d] = acc[j];
+            for (int j = 0; j < R; j++) *row_ptr(op, d, j) = acc[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j++)
+                if (j >= lead && j < in_left) *row_ptr(op, d, j) = acc[j];
         }
 #pragma unroll
         for (int j = 0; j < L - 1; j++) acc[j] = acc[j + R];
 #pragma unroll
         for (int j = L - 1; j < L - 1 + R; j++) acc[j] = 0.0;
+        const long long step = (long long)d * (8 * R);
+        if (!EDGE) { if (vp) vp += step; if (wp) wp += step; }
         pin += (long long)R * a.d;
+        op += step;
+        in_left -= R;
+        lead -= R;
     }
 }
 
 template <int L>
-__global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)) k_column_synthesis(const __grid_constant__ ColArgs a) {
-    constexpr int R = col_rows<L>::value;
+__global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_synthesis(const __grid_constant__ ColArgs a) {
+    constexpr bool ST = col_smem_taps_syn<L>::value;
+    __shared__ double2 s_taps[ST ? L : 1];
+    if (ST) {
+        if (threadIdx.x < L) s_taps[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
+        __syncthreads();
+    }
+    const uint32_t taps_addr = (uint32_t)__cvta_generic_to_shared(s_taps);
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
-    const long long col = gid & (a.d - 1);
+    const int d = (int)a.d;
+    const int col = (int)(gid & (a.d - 1));
     const long long chunk = gid / a.d;
     if (chunk >= a.chunks) return;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const double *v = a.x ? a.x + b * a.ldx : nullptr;
         const double *w = a.w_in ? a.w_in + b * a.ldw_in : nullptr;
-        double *out = a.v + b * a.ldv;
         const long long rows = (a.n_out - col + a.d - 1) / a.d;
         const long long o_start = chunk * a.rows_per_chunk;
-        const long long o_end = o_start + a.rows_per_chunk < rows ? o_start + a.rows_per_chunk : rows;
-        if (o_start >= o_end) continue;
+        const long long left64 = rows - o_start;
+        if (left64 <= 0) continue;
+        const int nout = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
         const long long pin0 = a.t0 + col + o_start * a.d;  // position of input row o_start (before stream offsets)
+        // the first block's outputs are chunk rows -(L-1) .. : start the output pointer there (never dereferenced below row 0)
+        char *op = reinterpret_cast<char *>(a.v + b * a.ldv + col + o_start * a.d) - (long long)d * (8 * (L - 1));
         const long long lo_off = a.off_h < a.off_g ? a.off_h : a.off_g, hi_off = a.off_h < a.off_g ? a.off_g : a.off_h;
-        const long long last_pos = pin0 + (o_end - o_start + L - 2) * a.d;
-        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false>(a, v, w, out, col, o_start, o_end, pin0);
-        else col_synth_chunk<L, true>(a, v, w, out, col, o_start, o_end, pin0);
+        const long long last_pos = pin0 + (long long)(nout + L - 2) * a.d;
+        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false>(a, v, w, op, d, nout, pin0, taps_addr);
+        else col_synth_chunk<L, true>(a, v, w, op, d, nout, pin0, taps_addr);
     }
 }
 
@@ -213,7 +321,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &g
     int64_t chunks = (want_threads + d * batch - 1) / (d * batch);
     if (chunks < 1) chunks = 1;
     int64_t rpc = (rows + chunks - 1) / chunks;
-    if (rpc < 32 * kCR) rpc = 32 * kCR;
+    if (rpc < 4 * kCR) rpc = 4 * kCR;
     rpc = ((rpc + kCR - 1) / kCR) * kCR;
     chunks = (rows + rpc - 1) / rpc;
     const int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;

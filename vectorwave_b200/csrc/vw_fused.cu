@@ -169,6 +169,82 @@ __device__ __forceinline__ void synthesis_item(const double *__restrict__ bot, i
     }
 }
 
+// ---- long filters: taps from shared memory -------------------------------------------------------------------
+// sm_100 ptxas feeds DFMA tap operands from uniform registers only (no constant-bank operand), and there are 63 of
+// them: from 16 taps on (32 doubles = 64 URs) it spills them to vector registers and refills with R2UR between the
+// DFMAs.  Long filters instead keep (h[k], g[k]) pairs at the front of shared memory; the item loops fetch the one
+// pair that enters the R-wide tap window per input step with a broadcast LDS.128 (volatile asm keeps the load at its
+// step instead of hoisted out of the item loop into 2L live registers).
+template <int L> struct smem_taps { static constexpr bool value = L >= 16; };
+constexpr int kTapBytes = VW_FUSED_MAX_L * 16;   // tap pairs live at the front of dynamic shared memory
+__device__ __forceinline__ void lds_tap_pair(uint32_t addr, double &h, double &g) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(h), "=d"(g) : "r"(addr));
+}
+__device__ __forceinline__ void lds_tap_one(uint32_t addr, double &h) {
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(h) : "r"(addr));
+}
+
+// analysis, step s = 0 .. R+L-2 reads in[top - s*d]; output r meets tap k = r - (R-1) + s, so tap s enters at step s
+template <int L, int R, bool WITH_G, bool FULL>
+__device__ __forceinline__ void analysis_item_st(const double *__restrict__ top, int d, int nvalid, uint32_t taps,
+                                                 double (&ah)[R], double (&ag)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
+    double th[L], tg[L];
+    const double *p = top;
+#pragma unroll
+    for (int s = 0; s <= R + L - 2; s++) {
+        const int m = R - 1 - s;
+        double xv;
+        if (FULL || m <= 0) xv = *p;
+        else xv = m < nvalid ? *p : 0.0;
+        p -= d;
+        if (s < L) {
+            if (WITH_G) lds_tap_pair(taps + 16u * s, th[s], tg[s]);
+            else lds_tap_one(taps + 16u * s, th[s]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r - m;
+            if (k >= 0 && k < L) {
+                ah[r] = fma(th[k], xv, ah[r]);
+                if (WITH_G) ag[r] = fma(tg[k], xv, ag[r]);
+            }
+        }
+    }
+}
+
+// synthesis, both streams in one walk: step m reads V[bot_v + m*d] and W[bot_w + m*d]; output r meets tap k = m - r
+template <int L, int R, bool FULL, bool HAVE_W>
+__device__ __forceinline__ void synthesis_item_st(const double *__restrict__ bv, const double *__restrict__ bw, int d,
+                                                  int nvalid, uint32_t taps, double (&acc)[R]) {
+    double th[L], tg[L];
+    const double *pv = bv, *pw = bw;
+#pragma unroll
+    for (int m = 0; m <= R + L - 2; m++) {
+        double xv, xw = 0.0;
+        if (FULL || m < L) { xv = *pv; if (HAVE_W) xw = *pw; }
+        else {
+            const bool live = m < nvalid + L - 1;
+            xv = live ? *pv : 0.0;
+            if (HAVE_W) xw = live ? *pw : 0.0;
+        }
+        pv += d; pw += d;
+        if (m < L) {
+            if (HAVE_W) lds_tap_pair(taps + 16u * m, th[m], tg[m]);
+            else lds_tap_one(taps + 16u * m, th[m]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = m - r;
+            if (k >= 0 && k < L) {
+                acc[r] = fma(th[k], xv, acc[r]);
+                if (HAVE_W) acc[r] = fma(tg[k], xw, acc[r]);
+            }
+        }
+    }
+}
+
 // runtime-L variants (filter lengths without a specialisation, L <= 32)
 template <int R, bool WITH_G>
 __device__ __forceinline__ void analysis_item_dyn(const double *__restrict__ in, int base, int d, int hi_clamp, int L,
@@ -227,13 +303,16 @@ struct InvArgs {
 // ------------------------------------------------------------------------------------------------
 // fused analysis
 // ------------------------------------------------------------------------------------------------
-// shared memory: [bufA: P][bufB: P][S0: T][S1: T] doubles (S only when use_stage), then one mbarrier
+// shared memory: [tap pairs: 512 B][bufA: P][bufB: P][S0: T][S1: T] doubles (S only when use_stage), then one mbarrier
 template <int L>
 __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_analysis(const __grid_constant__ FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;  // runtime filter length
     const int T = a.tile, HT = a.htot, P = T + HT;
-    double *buf0 = reinterpret_cast<double *>(smem_raw);
+    constexpr bool ST = smem_taps<L>::value;
+    const uint32_t taps = smem_u32(smem_raw);
+    if (ST && threadIdx.x < L) reinterpret_cast<double2 *>(smem_raw)[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
+    double *buf0 = reinterpret_cast<double *>(smem_raw + kTapBytes);
     double *buf1 = buf0 + P;
     double *stg0 = buf1 + P;
     double *stg1 = stg0 + (a.use_stage ? T : 0);
@@ -285,7 +364,15 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                 double ah[kR], ag[kR];
                 if (L > 0) {
                     constexpr int LL = L > 0 ? L : 2;
-                    if (part == 0) {
+                    if (ST) {
+                        if (part == 0) {
+                            if (full) analysis_item_st<LL, kR, false, true>(top, d, nvalid, taps, ah, ag);
+                            else analysis_item_st<LL, kR, false, false>(top, d, nvalid, taps, ah, ag);
+                        } else {
+                            if (full) analysis_item_st<LL, kR, true, true>(top, d, nvalid, taps, ah, ag);
+                            else analysis_item_st<LL, kR, true, false>(top, d, nvalid, taps, ah, ag);
+                        }
+                    } else if (part == 0) {
                         if (full) analysis_item<LL, kR, false, true>(top, d, nvalid, a.f, ah, ag);
                         else analysis_item<LL, kR, false, false>(top, d, nvalid, a.f, ah, ag);
                     } else {
@@ -363,13 +450,16 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
 // ------------------------------------------------------------------------------------------------
 // fused synthesis (index rule t + k*d: PERIODIC, ZERO_PADDING, linear span)
 // ------------------------------------------------------------------------------------------------
-// shared memory: [bufA: P][bufB: P][W0: P][W1: P] doubles, then three mbarriers (V, W0, W1)
+// shared memory: [tap pairs: 512 B][bufA: P][bufB: P][W0: P][W1: P] doubles, then three mbarriers (V, W0, W1)
 template <int L>
 __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_synthesis(const __grid_constant__ InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;
     const int T = a.tile, HT = a.htot, P = T + HT;
-    double *buf0 = reinterpret_cast<double *>(smem_raw);
+    constexpr bool ST = smem_taps<L>::value;
+    const uint32_t taps = smem_u32(smem_raw);
+    if (ST && threadIdx.x < L) reinterpret_cast<double2 *>(smem_raw)[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
+    double *buf0 = reinterpret_cast<double *>(smem_raw + kTapBytes);
     double *buf1 = buf0 + P;
     double *wb0 = buf1 + P, *wb1 = buf1 + 2 * P;
     uint64_t *bars = reinterpret_cast<uint64_t *>(buf1 + 3 * P);  // [0]=V, [1]=W0, [2]=W1
@@ -444,7 +534,15 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
             for (int r = 0; r < kR; r++) acc[r] = 0.0;
             if (L > 0) {
                 constexpr int LL = L > 0 ? L : 2;
-                if (full) {
+                if (ST) {
+                    if (full) {
+                        if (have_w) synthesis_item_st<LL, kR, true, true>(cur + base, wt + base, d, nvalid, taps, acc);
+                        else synthesis_item_st<LL, kR, true, false>(cur + base, wt + base, d, nvalid, taps, acc);
+                    } else {
+                        if (have_w) synthesis_item_st<LL, kR, false, true>(cur + base, wt + base, d, nvalid, taps, acc);
+                        else synthesis_item_st<LL, kR, false, false>(cur + base, wt + base, d, nvalid, taps, acc);
+                    }
+                } else if (full) {
                     synthesis_item<LL, kR, true>(cur + base, d, nvalid, a.f.h, acc);
                     if (have_w) synthesis_item<LL, kR, true>(wt + base, d, nvalid, a.f.g, acc);
                 } else {
@@ -511,8 +609,8 @@ int64_t even_up(int64_t v) { return (v + 1) & ~1ll; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
-    if (fwd) return (size_t)((2 * (tile + htot) + (use_stage ? 2 * tile : 0)) * 8 + 64);
-    return (size_t)(4 * (tile + htot) * 8 + 64);
+    if (fwd) return (size_t)((2 * (tile + htot) + (use_stage ? 2 * tile : 0)) * 8 + 64 + kTapBytes);
+    return (size_t)(4 * (tile + htot) * 8 + 64 + kTapBytes);
 }
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
