@@ -285,7 +285,7 @@ def main():
                 "inverse_achieved_gbs": alg_bytes_dir / inv_ms * 1e-6,
                 "fused_compulsory_bytes_per_direction": 8.0 * (levels + 2) * b * n,
                 "frac_of_fused_compulsory_bound": (8.0 * (levels + 2) * b * n / fwd_ms * 1e-6) / peak,
-                "fp64_fma_peak_tflops_measured": 34.1,
+                "fp64_fma_peak_tflops_measured": 37.0,   # tools/dfma_probe.cu on this pool: 63.7 DFMA/clk/SM at 1965 MHz
                 "fp64_tflops_achieved": 4.0 * hs.size * levels * b * n / fwd_ms * 1e-9}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):

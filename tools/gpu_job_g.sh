@@ -1,0 +1,3 @@
+python tools/quickbench.py --configs c4_haar,c4_db4,c4_sym8 --reps 3 --fuse 1 --colmin 3 > gpurun_out/memtest_a.jsonl 2>&1
+cat gpurun_out/memtest_a.jsonl
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_column|k_fused" -c 40 --csv --log-file gpurun_out/kern_r1o.csv python tools/quickbench.py --configs c4_haar,c4_sym8 --reps 1 --fuse 1 --colmin 3 > /dev/null 2>&1

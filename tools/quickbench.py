@@ -17,6 +17,9 @@ CONFIGS = {
     "c2s_db4": ("db4", 16, 4096, 4),
     "c3_sym8": ("sym8", 1024, 65536, 8),
     "c4_coif5": ("coif5", 1, 1 << 28, 10),
+    "c4_haar": ("haar", 1, 1 << 28, 10),
+    "c4_db4": ("db4", 1, 1 << 28, 10),
+    "c4_sym8": ("sym8", 1, 1 << 28, 10),
     "c5_db8": ("db8", 256, 1 << 20, 6),
 }
 
@@ -68,6 +71,7 @@ if __name__ == "__main__":
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--poly", type=int, default=1)
+    ap.add_argument("--colmin", type=int, default=0)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly}, a.mode)
+        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin}, a.mode)

@@ -14,7 +14,8 @@ from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentExcepti
                      NativeEngineError, NullPointerException)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvwmodwt.so")
+# VW_LIB_PATH: developer A/B builds of the same engine (csrc/Makefile TARGET=...); never a different implementation
+LIB_PATH = os.environ.get("VW_LIB_PATH") or os.path.join(_HERE, "libvwmodwt.so")
 
 FLAG_DEVICE_PTRS = 1 << 0
 FLAG_CHECK_FINITE = 1 << 1

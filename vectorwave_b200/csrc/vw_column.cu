@@ -13,6 +13,10 @@
 //             (MultiLevelMODWTTransform.java:554-645; sigma = -1 streams are run with reversed taps)
 #include "vw_internal.cuh"
 
+#ifndef VW_COL_VARIANT
+#define VW_COL_VARIANT 0
+#endif
+
 namespace {
 
 constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value
@@ -60,6 +64,16 @@ struct ColArgs {
 // the loops below keep one 64-bit byte pointer per stream that is bumped once per block, reach row r through
 // `ptr + d * (8 r)` (a single IMAD.WIDE with a 32-bit d), and use unpredicated loads / stores whenever a whole block
 // is in range.
+// Prefetch load that stays where it is written: NVVM otherwise sinks the next block's loads below the FMA block to
+// save registers, which leaves no time to cover the HBM latency (measured: 12 % of warp time on the first use).
+__device__ __forceinline__ double ldg_early(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// Two blocks ahead the rows are only pulled into L2 (no register cost); the register prefetch one block ahead then
+// sees L2 latency instead of loaded-HBM latency (> one block of FMAs at 4.6 TB/s).
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ const double *row_ptr(const char *base, int d, int r) {
     return reinterpret_cast<const double *>(base + (long long)d * (long long)(8 * r));
 }
@@ -69,7 +83,7 @@ __device__ __forceinline__ double *row_ptr(char *base, int d, int r) {
 
 // ---- analysis ------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysis(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4 : 3) k_column_analysis(const __grid_constant__ ColArgs a) {
     constexpr int R = col_rows<L>::value;
     constexpr bool ST = col_smem_taps<L>::value;
     __shared__ double2 s_taps[ST ? L : 1];
@@ -105,6 +119,20 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
 #pragma unroll
             for (int i = 0; i < L - 1; i++) seq[i] = ext_load<true>(x, p - (long long)(L - 1 - i) * a.d, a.n_in, a.mode);
         }
+#if VW_COL_VARIANT == 1
+        // variant 1: no register prefetch -- rows are loaded straight into the window; latency is covered by occupancy
+        auto load_rows = [&]() {
+            if (left >= R) {
+#pragma unroll
+                for (int r = 0; r < R; r++) seq[L - 1 + r] = ldg_early(row_ptr(xp, d, r));
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) seq[L - 1 + r] = r < left ? __ldg(row_ptr(xp, d, r)) : 0.0;
+            }
+        };
+        load_rows();
+        while (left > 0) {
+#else
         // software pipeline: the next block's rows are in flight while this block's FMAs run (output rows lie inside [0, n_in))
         double nxt[R];
         if (left >= R) {
@@ -119,11 +147,18 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
             for (int r = 0; r < R; r++) seq[L - 1 + r] = nxt[r];
             if (left >= 2 * R) {
 #pragma unroll
-                for (int r = 0; r < R; r++) nxt[r] = __ldg(row_ptr(xp, d, R + r));
+                for (int r = 0; r < R; r++) nxt[r] = ldg_early(row_ptr(xp, d, R + r));
+#if VW_COL_VARIANT == 2
+                if (left >= 3 * R) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) prefetch_l2(row_ptr(xp, d, 2 * R + r));
+                }
+#endif
             } else if (left > R) {
 #pragma unroll
                 for (int r = 0; r < R; r++) nxt[r] = R + r < left ? __ldg(row_ptr(xp, d, R + r)) : 0.0;
             }
+#endif
             double ah[R], ag[R];
 #pragma unroll
             for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
@@ -165,6 +200,9 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
             const long long step = (long long)d * (8 * R);
             xp += step; vp += step; wp += step;
             left -= R;
+#if VW_COL_VARIANT == 1
+            if (left > 0) load_rows();
+#endif
         }
     }
 }
@@ -193,8 +231,8 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
         if (!EDGE && avail >= R) {
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                nv[r] = v ? __ldg(row_ptr(vp, d, first + r)) : 0.0;
-                nw[r] = w ? __ldg(row_ptr(wp, d, first + r)) : 0.0;
+                nv[r] = v ? ldg_early(row_ptr(vp, d, first + r)) : 0.0;
+                nw[r] = w ? ldg_early(row_ptr(wp, d, first + r)) : 0.0;
             }
         } else {
 #pragma unroll
@@ -219,6 +257,15 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
 #pragma unroll
         for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = nw[r]; }
         if (in_left > R) load_block(R, in_left - R, nv, nw);
+#if VW_COL_VARIANT == 2
+        if (!EDGE && in_left >= 3 * R) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (v) prefetch_l2(row_ptr(vp, d, 2 * R + r));
+                if (w) prefetch_l2(row_ptr(wp, d, 2 * R + r));
+            }
+        }
+#endif
         if (col_smem_taps_syn<L>::value) {
 #pragma unroll
             for (int k = 0; k < L; k++) {
@@ -313,7 +360,7 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_synthes
     }
 
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &grid, int &rows_per_chunk, int &chunks_out) {
-    if (d < 32) return VW_EUNSUPPORTED;
+    if (d < 4 || d > (1ll << 30)) return VW_EUNSUPPORTED;   // below 4 a warp row access no longer covers whole sectors
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
     // L-1 warm-up rows each chunk re-reads
@@ -333,6 +380,11 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &g
 }
 
 }  // namespace
+
+int vw_column_min_level(const vw_ctx *ctx, int l) {
+    if (ctx->opt_colmin > 0) return (int)(ctx->opt_colmin < 3 ? 3 : ctx->opt_colmin);
+    return l >= 24 ? 3 : 6;
+}
 
 int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int64_t ldv, double *w, int64_t ldw,
                        int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode) {

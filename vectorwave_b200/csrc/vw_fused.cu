@@ -667,11 +667,19 @@ double group_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t
         *best_tile = std::min(t, ncap);
         return tile_cost(ctx, fwd, l, first, nf, *best_tile);
     }
+    // the launch equalises tiles over the row (ceil(n / ntiles)), so cost the tile that will really run
+    int64_t last_bal = -1;
     for (int64_t t = tmin; t <= 28672; t += 256) {
         const int64_t tt = std::min(t, ncap);
-        const double c = tile_cost(ctx, fwd, l, first, nf, tt);
-        if (c == INFINITY) break;
-        if (c < best * 0.985) { best = c; *best_tile = tt; }
+        const int64_t nt = ceil_div(n, tt);
+        int64_t bal = even_up(ceil_div(n, nt));
+        if (fwd && bal < htot) bal = tt;
+        if (bal != last_bal) {
+            last_bal = bal;
+            const double c = tile_cost(ctx, fwd, l, first, nf, bal);
+            if (c == INFINITY) { if (bal >= tt) break; else continue; }
+            if (c < best * 0.985) { best = c; *best_tile = bal; }
+        }
         if (tt == ncap) break;
     }
     return best;
@@ -691,7 +699,7 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
         for (int nf = 1; nf <= cap && done + nf <= levels; nf++) {
             int64_t tile;
             double c = group_cost(ctx, forward, l, done + 1, nf, n, &tile);
-            if (nf == 1 && done >= 5 && ctx->opt_poly != 0) {
+            if (nf == 1 && done + 1 >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
                 // deep single level (dilation >= 32): the column kernel streams 24 B/sample with no halo recompute
                 bool has = l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12 || l == 16 || l == 18 || l == 20 || l == 30;
                 const double ccol = std::max(2.0 * l / 64.0 / 0.70, 24.0 / 22.5 / 0.80) + 0.1;

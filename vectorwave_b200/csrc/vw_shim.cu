@@ -182,7 +182,7 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
             for (int level = g.first; level < g.first + g.nlev; level++) {
                 if ((rc = pick_out(level, vout, ld_vout))) return rc;
                 rc = VW_EUNSUPPORTED;
-                if (allow_fused && level >= 6 && ctx->opt_poly != 0) {
+                if (allow_fused && level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
                     rc = vw_column_analysis(ctx, cur, ld_cur, vout, ld_vout, w + (int64_t)(level - 1) * lsw, ldw, n, 0, n,
                                             batch, f, l, (int64_t)1 << (level - 1), mode);
                     if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
@@ -249,7 +249,7 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
                 if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
                 rc = VW_EUNSUPPORTED;
-                if (!exact && !(flags & VW_FLAG_NO_FUSE) && level >= 6 && ctx->opt_poly != 0) {
+                if (!exact && !(flags & VW_FLAG_NO_FUSE) && level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
                     rc = vw_column_synthesis(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
                                              (int64_t)1 << (level - 1), mode, al);
                     if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
@@ -361,6 +361,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;
     else if (!strcmp(name, "threads")) ctx->opt_threads = value;
     else if (!strcmp(name, "poly")) ctx->opt_poly = value;
+    else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
     return VW_OK;
 }
@@ -737,7 +738,7 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
             // analysis over input coords: in = cur (position cur_off at index 0), outputs [start, n_in)
             // W rows only exist for the span: write them via a second launch restricted to [halo, n_in)
             rc = VW_EUNSUPPORTED;
-            if (last && nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= 32 && ctx->opt_poly != 0) {
+            if (last && nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= ((int64_t)1 << (vw_column_min_level(ctx, l) - 1)) && ctx->opt_poly != 0) {
                 rc = vw_column_analysis(ctx, cur, 0, vout, 0, w, 0, n_in, halo, n_local, 1, f, l, d, VW_MODE_LINEAR);
                 if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
             }
@@ -797,7 +798,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                 dst = (double *)p;
             }
             rc = VW_EUNSUPPORTED;
-            if (nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= 32 && ctx->opt_poly != 0) {
+            if (nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= ((int64_t)1 << (vw_column_min_level(ctx, l) - 1)) && ctx->opt_poly != 0) {
                 rc = vw_column_synthesis(ctx, cur, 0, w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d, VW_MODE_LINEAR, default_align());
                 if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
             }
