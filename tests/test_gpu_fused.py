@@ -40,9 +40,12 @@ def _check_forward(eng, x, name, levels, mode, flags=0):
 
 
 def _check_inverse(eng, w, v, name, mode, x):
+    from vectorwave_b200.modwt import multilevel_alignment
     h, g, wid = filters(name)
-    order = _native.ORDER_PAIR if mode == 1 else _native.ORDER_SPLIT
-    xr = np.asarray(eng.inverse(w, v, h * S, g * S, mode, None, order))
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    # SYMMETRIC: per-level (sigma, tau) from SymmetricAlignmentStrategy -> aligned tile stage (d < 4) + column kernels
+    align, order = multilevel_alignment(vw.get_wavelet(name), bm, w.shape[0])
+    xr = np.asarray(eng.inverse(w, v, h * S, g * S, mode, align, order))
     for i in range(v.shape[0]):
         ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, wid)
         np.testing.assert_allclose(xr[i], ref, rtol=0, atol=tol(x))
@@ -57,8 +60,7 @@ def test_every_specialised_filter_length_multi_tile(eng, mode, name):
     x = rng.standard_normal((3, n))
     levels = min(6, cref.max_levels(n, len(filters(name)[0]), 0))
     w, v = _check_forward(eng, x, name, levels, mode)
-    if mode != 2:   # the fused synthesis covers PERIODIC / ZERO_PADDING; SYMMETRIC uses the per-level kernels
-        _check_inverse(eng, w, v, name, mode, x)
+    _check_inverse(eng, w, v, name, mode, x)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
@@ -88,8 +90,7 @@ def test_forced_tiles_and_fuse_depths(eng, mode, tile, fuse):
     for name, n, levels in (("db4", 4096, 4), ("haar", 3000, 7), ("sym8", 9002, 5)):
         x = rng.standard_normal((2, n))
         w, v = _check_forward(eng, x, name, levels, mode)
-        if mode != 2:
-            _check_inverse(eng, w, v, name, mode, x)
+        _check_inverse(eng, w, v, name, mode, x)
 
 
 def test_odd_lengths_and_strided_rows_fall_back_correctly(eng):
@@ -98,8 +99,7 @@ def test_odd_lengths_and_strided_rows_fall_back_correctly(eng):
         x = rng.standard_normal((2, n))
         for mode in (0, 1, 2):
             w, v = _check_forward(eng, x, "db4", 4, mode)
-            if mode != 2:
-                _check_inverse(eng, w, v, "db4", mode, x)
+            _check_inverse(eng, w, v, "db4", mode, x)
     # row stride larger than n (ld != n), even and odd
     for ld in (4100, 4101):
         big = rng.standard_normal((3, ld))

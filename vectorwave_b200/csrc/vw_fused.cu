@@ -297,7 +297,8 @@ struct InvArgs {
     long long n_in, n_out, batch;
     int tile, htot, nlev, log2d0, mode, tiles_per_row, use_tma, lrt;
     const double *thr; int thr_per_row, thr_soft;
-    VwFilt32 f;
+    long long off_v, off_w;   // stream offsets of an aligned single-level stage (SYMMETRIC sigma/tau); 0 otherwise
+    VwFilt32 f;               // taps of a sigma = -1 stream arrive reversed
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -484,11 +485,15 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
     const int top = a.nlev - 1;
     const double *vrow = a.v ? a.v + b * a.ldv : nullptr;
     auto stage_count = [&](int lev) { int e = extent(lev); return a.use_tma ? ((e + 1) & ~1) : e; };  // bulk copies move 16-byte units
-    stage_tile(buf0, vrow, g0, stage_count(top), a.n_in, a.mode, a.use_tma, &bars[0], vrow == nullptr);
+    // aligned single-level stages read V from g0 + off_v and W from g0 + off_w; staging starts on an even position
+    // (bulk copies move 16-byte units) and the item loops skip the parity sample
+    const int par_v = (int)((g0 + a.off_v) & 1), par_w = (int)((g0 + a.off_w) & 1);
+    stage_tile(buf0, vrow, g0 + a.off_v - par_v, stage_count(top) + 2 * par_v, a.n_in, a.mode, a.use_tma, &bars[0], vrow == nullptr);
     auto stage_w = [&](int lev, int slot) {
         const bool have = (a.detail_mask >> lev) & 1ull;
         const double *wrow = have ? a.w + (long long)lev * a.lsw + b * a.ldw : nullptr;
-        stage_tile(slot ? wb1 : wb0, wrow, g0, stage_count(lev), a.n_in, a.mode, a.use_tma, &bars[1 + slot], !have);
+        stage_tile(slot ? wb1 : wb0, wrow, g0 + a.off_w - par_w, stage_count(lev) + 2 * par_w, a.n_in, a.mode, a.use_tma,
+                   &bars[1 + slot], !have);
     };
     stage_w(top, top & 1);
     if (a.use_tma) mbar_wait(&bars[0], 0);
@@ -504,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         }
         __syncthreads();
         const bool have_w = (a.detail_mask >> lev) & 1ull;
-        double *wt = slot ? wb1 : wb0;
+        double *wt = (slot ? wb1 : wb0) + par_w;
+        const double *cv = cur + (lev == top ? par_v : 0);
         const int in_ext = extent(lev);
         if (a.thr && have_w) {
             // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118)
@@ -536,21 +542,21 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                 constexpr int LL = L > 0 ? L : 2;
                 if (ST) {
                     if (full) {
-                        if (have_w) synthesis_item_st<LL, kR, true, true>(cur + base, wt + base, d, nvalid, taps, acc);
-                        else synthesis_item_st<LL, kR, true, false>(cur + base, wt + base, d, nvalid, taps, acc);
+                        if (have_w) synthesis_item_st<LL, kR, true, true>(cv + base, wt + base, d, nvalid, taps, acc);
+                        else synthesis_item_st<LL, kR, true, false>(cv + base, wt + base, d, nvalid, taps, acc);
                     } else {
-                        if (have_w) synthesis_item_st<LL, kR, false, true>(cur + base, wt + base, d, nvalid, taps, acc);
-                        else synthesis_item_st<LL, kR, false, false>(cur + base, wt + base, d, nvalid, taps, acc);
+                        if (have_w) synthesis_item_st<LL, kR, false, true>(cv + base, wt + base, d, nvalid, taps, acc);
+                        else synthesis_item_st<LL, kR, false, false>(cv + base, wt + base, d, nvalid, taps, acc);
                     }
                 } else if (full) {
-                    synthesis_item<LL, kR, true>(cur + base, d, nvalid, a.f.h, acc);
+                    synthesis_item<LL, kR, true>(cv + base, d, nvalid, a.f.h, acc);
                     if (have_w) synthesis_item<LL, kR, true>(wt + base, d, nvalid, a.f.g, acc);
                 } else {
-                    synthesis_item<LL, kR, false>(cur + base, d, nvalid, a.f.h, acc);
+                    synthesis_item<LL, kR, false>(cv + base, d, nvalid, a.f.h, acc);
                     if (have_w) synthesis_item<LL, kR, false>(wt + base, d, nvalid, a.f.g, acc);
                 }
             } else {
-                synthesis_item_dyn<kR>(cur, base, d, in_ext - 1, LR, a.f.h, acc);
+                synthesis_item_dyn<kR>(cv, base, d, in_ext - 1, LR, a.f.h, acc);
                 if (have_w) synthesis_item_dyn<kR>(wt, base, d, in_ext - 1, LR, a.f.g, acc);
             }
             double *q = nxt + base;
@@ -768,10 +774,12 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
 
 int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     if (p.l < 2 || p.l > VW_FUSED_MAX_L || p.nlevels < 1 || p.batch < 1 || p.n_out < 1) return VW_EUNSUPPORTED;
-    if (p.mode == VW_SYMMETRIC) return VW_EUNSUPPORTED;  // two-sided alignment: per-level kernels
+    const bool aligned_stage = p.has_align;   // general (sigma, tau) alignment: one level per launch
+    if (aligned_stage && p.nlevels != 1) return VW_EUNSUPPORTED;
+    if (p.mode == VW_SYMMETRIC && !aligned_stage) return VW_EUNSUPPORTED;
     const int64_t d0 = 1ll << (p.first_level - 1);
     const int64_t hexact = (int64_t)(p.l - 1) * d0 * ((1ll << p.nlevels) - 1);
-    const int64_t htot = (hexact + 1) & ~1ll;
+    const int64_t htot = ((hexact + 1) & ~1ll) + (aligned_stage ? 4 : 0);   // room for the parity sample of odd stream offsets
     if (hexact > p.n_in || htot > 12288) return VW_EUNSUPPORTED;
     if (p.first_level + p.nlevels - 1 > 30) return VW_EUNSUPPORTED;
     const bool use_tma = (!p.v || aligned16(p.v)) && aligned16(p.w) && aligned16(p.out) && !(p.ldv & 1) && !(p.ldw & 1) &&
@@ -796,7 +804,18 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     a.tile = (int)tile; a.htot = (int)htot; a.nlev = p.nlevels; a.log2d0 = p.first_level - 1; a.mode = p.mode;
     a.tiles_per_row = (int)tiles_per_row; a.use_tma = use_tma; a.lrt = p.l;
     a.thr = p.thr_dev; a.thr_per_row = p.thr_per_row; a.thr_soft = p.thr_soft;
-    for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
+    a.off_v = a.off_w = 0;
+    bool rev_h = false, rev_g = false;
+    if (aligned_stage) {
+        // sigma=+1: sum_k f[k] S[t - tau + k d];  sigma=-1: sum_k f[k] S[t + tau - k d] = sum_k' f[L-1-k'] S[t + tau - (L-1) d + k' d]
+        rev_h = p.align.sigma_h < 0; rev_g = p.align.sigma_g < 0;
+        a.off_v = rev_h ? (int64_t)p.align.tau_h - (int64_t)(p.l - 1) * d0 : -(int64_t)p.align.tau_h;
+        a.off_w = rev_g ? (int64_t)p.align.tau_g - (int64_t)(p.l - 1) * d0 : -(int64_t)p.align.tau_g;
+    }
+    for (int k = 0; k < VW_FUSED_MAX_L; k++) {
+        a.f.h[k] = k < p.l ? (rev_h ? f.h[p.l - 1 - k] : f.h[k]) : 0.0;
+        a.f.g[k] = k < p.l ? (rev_g ? f.g[p.l - 1 - k] : f.g[k]) : 0.0;
+    }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
     const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;

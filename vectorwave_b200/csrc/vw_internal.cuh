@@ -82,6 +82,8 @@ struct VwFusedInv {
     int l, first_level, nlevels, mode;
     const double *thr_dev; int thr_per_row; int thr_soft;  // optional fused thresholding of W on load
     int64_t tile;                            // 0 = choose here
+    bool has_align = false;                  // single-level stage with a general (sigma, tau) alignment (any mode)
+    vw_align align = {1, 0, 1, 0};
 };
 
 // Level schedule: which consecutive levels share one fused launch and with which tile, from a small cost model

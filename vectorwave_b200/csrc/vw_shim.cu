@@ -249,9 +249,21 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
                 if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
                 rc = VW_EUNSUPPORTED;
-                if (!exact && !(flags & VW_FLAG_NO_FUSE) && level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
+                const bool fast = !exact && !(flags & VW_FLAG_NO_FUSE);
+                // aligned (sigma, tau) stages have no multi-level fused form: column kernels from dilation 4, and the
+                // single-level tile kernel (stream offsets + reversed taps) below that
+                const int col_min = allow_fused ? vw_column_min_level(ctx, l) : std::min(3, vw_column_min_level(ctx, l));
+                if (fast && level >= col_min && ctx->opt_poly != 0) {
                     rc = vw_column_synthesis(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
                                              (int64_t)1 << (level - 1), mode, al);
+                    if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+                }
+                if (rc == VW_EUNSUPPORTED && fast && !allow_fused) {
+                    VwFusedInv p{cur, ld_cur, w + (int64_t)(level - 1) * lsw, ldw, lsw, wj ? 1ull : 0ull, out, ld_out, batch, n, n,
+                                 l, level, 1, mode, nullptr, 0, 0, 0};
+                    p.has_align = true;
+                    p.align = al;
+                    rc = vw_fused_inverse(ctx, p, f);
                     if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
                 }
                 if (rc == VW_EUNSUPPORTED)
