@@ -253,6 +253,17 @@ def test_exact_median_selection_edge_cases():
     got = eng.universal_threshold(rows)
     for i in range(7):
         assert got[i] == pytest.approx(cref.universal_threshold(rows[i]), rel=1e-14)
+    # candidate-buffer overflow (every key in one 24-bit bucket) falls back to full-row passes: constant rows, heavy ties
+    for w1 in (np.full(200000, 1.2345), np.repeat(rng.standard_normal(7), 30000),
+               np.concatenate([np.full(100000, 1.0), np.full(100000, 2.0)]),            # the two middle ranks in different buckets
+               np.concatenate([np.full(70000, 0.5), 0.5 + 1e-13 * rng.random(60001), np.full(70000, 3.0)]),
+               rng.standard_normal(1 << 22) * 1e-3, np.abs(rng.standard_cauchy(300001))):
+        assert eng.universal_threshold(w1) == pytest.approx(cref.universal_threshold(w1), rel=1e-14, abs=0)
+    rows = np.stack([rng.standard_normal(65536), np.full(65536, -7.0), rng.standard_normal(65536) * 1e200,
+                     np.where(rng.random(65536) < 0.5, 1.0, 1.0 + 2.0 ** -30)])
+    got = eng.universal_threshold(rows)
+    for i in range(rows.shape[0]):
+        assert got[i] == pytest.approx(cref.universal_threshold(rows[i]), rel=1e-14, abs=0)
 
 
 # ---- device-resident path ------------------------------------------------------------------------------------------

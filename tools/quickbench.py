@@ -24,7 +24,7 @@ CONFIGS = {
 }
 
 
-def run(name, reps, opts, mode=0):
+def run(name, reps, opts, mode=0, denoise=False):
     wname, b, n, levels = CONFIGS[name]
     eng = vw.Engine.get()
     for k, v in opts.items():
@@ -57,6 +57,24 @@ def run(name, reps, opts, mode=0):
         out[label + "_gsamples"] = round(b * n / ms * 1e-6, 2)
         out[label + "_gbs_alg"] = round(24.0 * levels * b * n / ms * 1e-6, 1)
         out[label + "_launches"] = (eng.launch_count() - l0) // reps
+    if denoise:
+        y = torch.empty_like(x)
+        def den():
+            eng.denoise(x, hs, gs, levels, mode, None, order, -1.0, True)
+        for _ in range(2):
+            den()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record()
+        for _ in range(reps):
+            den()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["denoise_ms"] = round(ms, 4)
+        out["denoise_gsamples"] = round(b * n / ms * 1e-6, 2)
+        out["denoise_launches"] = (eng.launch_count() - l0) // reps
     out["fwdinv_gsamples"] = round(b * n / (out["fwd_ms"] + out["inv_ms"]) * 1e-6, 2)
     out["rt_err"] = float((xr - x).abs().max())
     print(json.dumps(out), flush=True)
@@ -72,6 +90,7 @@ if __name__ == "__main__":
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--poly", type=int, default=1)
     ap.add_argument("--colmin", type=int, default=0)
+    ap.add_argument("--denoise", type=int, default=0)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin}, a.mode)
+        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin}, a.mode, bool(a.denoise))

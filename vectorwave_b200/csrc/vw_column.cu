@@ -55,6 +55,7 @@ struct ColArgs {
     long long n_in, t0, n_out, batch, d;     // outputs cover positions [t0, t0+n_out) of the input coordinate system
     long long off_h, off_g;                  // synthesis stream offsets (see below)
     int rows_per_chunk, chunks, mode;
+    const double *thr; int thr_per_row, thr_soft;   // synthesis: threshold W on load (SWT denoise); thr == nullptr: off
     VwFilt32 f;                              // synthesis: taps already reversed for sigma = -1 streams
 };
 
@@ -216,7 +217,8 @@ __global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4
 // output rows [iR-(L-1), iR-(L-1)+R).
 template <int L, bool EDGE>
 __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *__restrict__ v, const double *__restrict__ w,
-                                                char *op, int d, int nout, long long pin, uint32_t taps_addr) {
+                                                char *op, int d, int nout, long long pin, uint32_t taps_addr, bool thr_on,
+                                                double lam) {
     constexpr int R = col_rows_syn<L>::value;
     // acc[j] <-> output row  m0 - (L-1) + j ; rows below 0 are never emitted
     double acc[L - 1 + R];
@@ -255,7 +257,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
     while (in_left > 0) {
         double cv[R], cw[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = nw[r]; }
+        for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = thr_on ? vw_threshold_value(nw[r], lam, a.thr_soft) : nw[r]; }
         if (in_left > R) load_block(R, in_left - R, nv, nw);
 #if VW_COL_VARIANT == 2
         if (!EDGE && in_left >= 3 * R) {
@@ -339,8 +341,10 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_synthes
         char *op = reinterpret_cast<char *>(a.v + b * a.ldv + col + o_start * a.d) - (long long)d * (8 * (L - 1));
         const long long lo_off = a.off_h < a.off_g ? a.off_h : a.off_g, hi_off = a.off_h < a.off_g ? a.off_g : a.off_h;
         const long long last_pos = pin0 + (long long)(nout + L - 2) * a.d;
-        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false>(a, v, w, op, d, nout, pin0, taps_addr);
-        else col_synth_chunk<L, true>(a, v, w, op, d, nout, pin0, taps_addr);
+        const bool thr_on = a.thr != nullptr && w != nullptr;
+        const double lam = thr_on ? a.thr[a.thr_per_row ? b : 0] : 0.0;
+        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
+        else col_synth_chunk<L, true>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
     }
 }
 
@@ -394,6 +398,7 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
     int rc = geometry(ctx, n_out, d, batch, grid, a.rows_per_chunk, a.chunks);
     if (rc) return rc;
     a.x = x; a.ldx = ldx; a.w_in = nullptr; a.ldw_in = 0; a.v = v; a.ldv = ldv; a.w = w; a.ldw = ldw;
+    a.thr = nullptr; a.thr_per_row = 0; a.thr_soft = 0;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.off_h = a.off_g = 0;
     a.mode = mode;
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < l ? f.h[k] : 0.0; a.f.g[k] = k < l ? f.g[k] : 0.0; }
@@ -406,13 +411,14 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
 
 int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double *w, int64_t ldw, double *out, int64_t ldo,
                         int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode,
-                        vw_align al) {
+                        vw_align al, const double *thr_dev, int thr_per_row, int thr_soft) {
     if (l < 2 || l > VW_FUSED_MAX_L || n_out < 1 || batch < 1) return VW_EUNSUPPORTED;
     ColArgs a;
     dim3 grid;
     int rc = geometry(ctx, n_out, d, batch, grid, a.rows_per_chunk, a.chunks);
     if (rc) return rc;
     a.x = v; a.ldx = ldv; a.w_in = w; a.ldw_in = ldw; a.v = out; a.ldv = ldo; a.w = nullptr; a.ldw = 0;
+    a.thr = thr_dev; a.thr_per_row = thr_per_row; a.thr_soft = thr_soft;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d;
     a.mode = mode;
     // sigma=+1: sum_k f[k] S[p - tau + k d];  sigma=-1: sum_k f[k] S[p + tau - k d] = sum_k' f[L-1-k'] S[p + tau - (L-1)d + k' d]

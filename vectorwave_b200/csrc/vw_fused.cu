@@ -516,10 +516,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
             // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118)
             const double lam = a.thr[a.thr_per_row ? b : 0];
             for (int i = tid; i < in_ext; i += (int)blockDim.x) {
-                const double c = wt[i], ab = fabs(c), m = ab - lam;
-                double r;
-                if (a.thr_soft) r = ab > lam ? (c > 0.0 ? m : (c < 0.0 ? -m : c * m)) : 0.0;
-                else r = ab <= lam ? 0.0 : c;
+                const double r = vw_threshold_value(wt[i], lam, a.thr_soft);
                 wt[i] = r;
             }
             __syncthreads();

@@ -120,13 +120,7 @@ k_threshold(double *__restrict__ c, int64_t batch, int64_t n, int64_t ld, const 
     if (t >= n) return;
     for (int64_t b = blockIdx.y; b < batch; b += gridDim.y) {
         double lam = thr[per_row ? b : 0];
-        double x = c[b * ld + t], a = fabs(x), r;
-        if (soft) {
-            double m = a - lam;  // Math.signum(x) * (|x| - lam); signum(+-0) = +-0 matters for lam < 0 only
-            r = a > lam ? (x > 0.0 ? m : (x < 0.0 ? -m : x * m)) : 0.0;
-        } else {
-            r = a <= lam ? 0.0 : x;
-        }
+        const double r = vw_threshold_value(c[b * ld + t], lam, soft);
         c[b * ld + t] = r;
     }
 }

@@ -42,6 +42,17 @@ struct vw_ctx {
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)
 };
 
+// MutableMultiLevelMODWTResult.applyThresholdToArray (CORE/modwt/MutableMultiLevelMODWTResult.java:97-118):
+// soft: |c| > t ? Math.signum(c) * (|c| - t) : 0;  hard: |c| <= t ? 0 : c.  One definition for every kernel that
+// thresholds on the fly.
+#ifdef __CUDACC__
+__device__ __forceinline__ double vw_threshold_value(double c, double lam, int soft) {
+    const double a = fabs(c), m = a - lam;
+    if (soft) return a > lam ? (c > 0.0 ? m : (c < 0.0 ? -m : c * m)) : 0.0;
+    return a <= lam ? 0.0 : c;
+}
+#endif
+
 int vw_fail(vw_ctx *ctx, int status, const char *fmt, ...);
 int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what);
 int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out);
@@ -102,7 +113,7 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
                        int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode);
 int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double *w, int64_t ldw, double *out, int64_t ldo,
                         int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode,
-                        vw_align al);
+                        vw_align al, const double *thr_dev = nullptr, int thr_per_row = 0, int thr_soft = 0);
 
 // ---- exact order statistics (vw_select.cu) ---------------------------------------------------
 // median(|w1|) per row -> universal thresholds written to thr_dev[batch] (device).

@@ -247,7 +247,6 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 if ((rc = pick_out(level, out, ld_out))) return rc;
                 vw_align al = align ? align[level - 1] : default_align();
                 const double *wj = ((detail_mask >> (level - 1)) & 1ull) ? w + (int64_t)(level - 1) * lsw : nullptr;
-                if (thr_dev && wj) return vw_fail(ctx, VW_ESTATE, "internal: unfused path requires pre-thresholded details");
                 rc = VW_EUNSUPPORTED;
                 const bool fast = !exact && !(flags & VW_FLAG_NO_FUSE);
                 // aligned (sigma, tau) stages have no multi-level fused form: column kernels from dilation 4, and the
@@ -255,20 +254,26 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 const int col_min = allow_fused ? vw_column_min_level(ctx, l) : std::min(3, vw_column_min_level(ctx, l));
                 if (fast && level >= col_min && ctx->opt_poly != 0) {
                     rc = vw_column_synthesis(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
-                                             (int64_t)1 << (level - 1), mode, al);
+                                             (int64_t)1 << (level - 1), mode, al, thr_dev, thr_per_row, thr_soft);
                     if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
                 }
                 if (rc == VW_EUNSUPPORTED && fast && !allow_fused) {
                     VwFusedInv p{cur, ld_cur, w + (int64_t)(level - 1) * lsw, ldw, lsw, wj ? 1ull : 0ull, out, ld_out, batch, n, n,
-                                 l, level, 1, mode, nullptr, 0, 0, 0};
+                                 l, level, 1, mode, thr_dev, thr_per_row, thr_soft, 0};
                     p.has_align = true;
                     p.align = al;
                     rc = vw_fused_inverse(ctx, p, f);
                     if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
                 }
-                if (rc == VW_EUNSUPPORTED)
+                if (rc == VW_EUNSUPPORTED) {
+                    // the per-level kernels have no threshold-on-load: threshold this level in place first (only
+                    // vw_swt_denoise passes thr_dev, and its W is engine scratch)
+                    if (thr_dev && wj &&
+                        (rc = vw_launch_threshold(ctx, const_cast<double *>(wj), batch, n, ldw, thr_dev, thr_per_row, thr_soft)))
+                        return rc;
                     rc = vw_launch_synthesis_level(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
                                                    (int64_t)1 << (level - 1), mode, al, order == VW_ORDER_PAIR, exact);
+                }
                 if (rc) return rc;
                 cur = out; ld_cur = ld_out; pp ^= 1;
             }
@@ -664,14 +669,12 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
         cudaMemcpyAsync(thr_dev, &threshold, 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);  // &threshold is a stack address
     }
-    // threshold all detail levels in place (one launch over [levels*batch] rows), then reconstruct
-    if (per_row) {
-        for (int j = 0; j < levels; j++)
-            if ((rc = vw_launch_threshold(ctx, wd + (size_t)j * bn, batch, n, n, thr_dev, 1, soft))) return rc;
-    } else if ((rc = vw_launch_threshold(ctx, wd, (int64_t)levels * batch, n, n, thr_dev, 0, soft))) return rc;
+    // reconstruct; the thresholding rides on the synthesis: fused stages threshold W while it sits in shared memory
+    // (MutableMultiLevelMODWTResult.applyThreshold :97-118 fused into the load), the other stages threshold their
+    // level in place just before consuming it
     uint64_t mask = levels >= 64 ? ~0ull : ((1ull << levels) - 1);
     if ((rc = inverse_device(ctx, wd, n, (int64_t)bn, vd, n, batch, n, f, l, levels, mode, align, order, mask, 1, od,
-                             ldod, flags, nullptr, 0, 0))) return rc;
+                             ldod, flags, thr_dev, per_row, soft))) return rc;
     if (!dev) if ((rc = copy_rows(ctx, out, ldo, od, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
     if (thresholds_out) {
         if (per_row) cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
