@@ -13,15 +13,13 @@
 //             (MultiLevelMODWTTransform.java:554-645; sigma = -1 streams are run with reversed taps)
 #include "vw_internal.cuh"
 
-#ifndef VW_COL_VARIANT
-#define VW_COL_VARIANT 0
-#endif
-
 namespace {
 
 constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value
 template <int L> struct col_rows { static constexpr int value = L >= 24 ? 8 : 9; };       // analysis
-template <int L> struct col_rows_syn { static constexpr int value = L >= 24 ? 6 : (L >= 16 ? 8 : 9); };  // synthesis (L-1+R sums)
+// synthesis keeps L-1+R running sums: long filters take R = 10 at two CTAs per SM (254 registers, no spills) -- fewer
+// window shifts per FMA beat the third CTA (measured on coif5)
+template <int L> struct col_rows_syn { static constexpr int value = L >= 24 ? 10 : (L >= 16 ? 8 : 9); };
 constexpr int kCThreads = 128;
 
 // Tap delivery.  sm_100 ptxas never folds a constant-bank operand into DFMA: taps go through uniform registers, and
@@ -72,9 +70,6 @@ __device__ __forceinline__ double ldg_early(const double *p) {
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-// Two blocks ahead the rows are only pulled into L2 (no register cost); the register prefetch one block ahead then
-// sees L2 latency instead of loaded-HBM latency (> one block of FMAs at 4.6 TB/s).
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ const double *row_ptr(const char *base, int d, int r) {
     return reinterpret_cast<const double *>(base + (long long)d * (long long)(8 * r));
 }
@@ -84,7 +79,7 @@ __device__ __forceinline__ double *row_ptr(char *base, int d, int r) {
 
 // ---- analysis ------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4 : 3) k_column_analysis(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysis(const __grid_constant__ ColArgs a) {
     constexpr int R = col_rows<L>::value;
     constexpr bool ST = col_smem_taps<L>::value;
     __shared__ double2 s_taps[ST ? L : 1];
@@ -120,20 +115,6 @@ __global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4
 #pragma unroll
             for (int i = 0; i < L - 1; i++) seq[i] = ext_load<true>(x, p - (long long)(L - 1 - i) * a.d, a.n_in, a.mode);
         }
-#if VW_COL_VARIANT == 1
-        // variant 1: no register prefetch -- rows are loaded straight into the window; latency is covered by occupancy
-        auto load_rows = [&]() {
-            if (left >= R) {
-#pragma unroll
-                for (int r = 0; r < R; r++) seq[L - 1 + r] = ldg_early(row_ptr(xp, d, r));
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) seq[L - 1 + r] = r < left ? __ldg(row_ptr(xp, d, r)) : 0.0;
-            }
-        };
-        load_rows();
-        while (left > 0) {
-#else
         // software pipeline: the next block's rows are in flight while this block's FMAs run (output rows lie inside [0, n_in))
         double nxt[R];
         if (left >= R) {
@@ -149,17 +130,10 @@ __global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4
             if (left >= 2 * R) {
 #pragma unroll
                 for (int r = 0; r < R; r++) nxt[r] = ldg_early(row_ptr(xp, d, R + r));
-#if VW_COL_VARIANT == 2
-                if (left >= 3 * R) {
-#pragma unroll
-                    for (int r = 0; r < R; r++) prefetch_l2(row_ptr(xp, d, 2 * R + r));
-                }
-#endif
             } else if (left > R) {
 #pragma unroll
                 for (int r = 0; r < R; r++) nxt[r] = R + r < left ? __ldg(row_ptr(xp, d, R + r)) : 0.0;
             }
-#endif
             double ah[R], ag[R];
 #pragma unroll
             for (int r = 0; r < R; r++) { ah[r] = 0.0; ag[r] = 0.0; }
@@ -201,9 +175,6 @@ __global__ void __launch_bounds__(kCThreads, (VW_COL_VARIANT == 1 || L < 16) ? 4
             const long long step = (long long)d * (8 * R);
             xp += step; vp += step; wp += step;
             left -= R;
-#if VW_COL_VARIANT == 1
-            if (left > 0) load_rows();
-#endif
         }
     }
 }
@@ -259,15 +230,6 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
 #pragma unroll
         for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = thr_on ? vw_threshold_value(nw[r], lam, a.thr_soft) : nw[r]; }
         if (in_left > R) load_block(R, in_left - R, nv, nw);
-#if VW_COL_VARIANT == 2
-        if (!EDGE && in_left >= 3 * R) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (v) prefetch_l2(row_ptr(vp, d, 2 * R + r));
-                if (w) prefetch_l2(row_ptr(wp, d, 2 * R + r));
-            }
-        }
-#endif
         if (col_smem_taps_syn<L>::value) {
 #pragma unroll
             for (int k = 0; k < L; k++) {
@@ -315,7 +277,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
 }
 
 template <int L>
-__global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_synthesis(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)) k_column_synthesis(const __grid_constant__ ColArgs a) {
     constexpr bool ST = col_smem_taps_syn<L>::value;
     __shared__ double2 s_taps[ST ? L : 1];
     if (ST) {

@@ -706,7 +706,7 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
                 // deep single level (dilation >= 32): the column kernel streams 24 B/sample with no halo recompute
                 bool has = l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12 || l == 16 || l == 18 || l == 20 || l == 30;
                 const double ccol = std::max(2.0 * l / 64.0 / 0.70, 24.0 / 22.5 / 0.80) + 0.1;
-                if (has && ccol < c) { c = ccol; tile = -2; }
+                if (has && (ccol < c || ctx->opt_poly == 2)) { c = ctx->opt_poly == 2 ? 0.01 : ccol; tile = -2; }   // poly = 2: force (diagnostics)
             }
             if (c == INFINITY) { if (nf > 1) continue; c = kGeneric; tile = -1; }
             if (best[done] + c < best[done + nf]) {
