@@ -649,7 +649,9 @@ double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t 
     }
     if (fwd) bytes = 8.0 * (double)(t + htot) + 8.0 * (double)t * (nf + 1);
     else bytes += 8.0 * (double)(t + htot) + 8.0 * (double)t;
-    const double c = dfma / 64.0 / 0.80;          // FP64 pipe: 64 DFMA/clk/SM, ~80 % reachable
+    // FP64 pipe: 64 DFMA/clk/SM.  Taps in uniform registers (l <= 12) reach ~80 % of it inside the item loops; taps in
+    // vector registers (l >= 16, three register operands per DFMA) top out at 52/clk (tools/dfma_probe.cu), ~62 % net
+    const double c = dfma / 64.0 / (l < 24 ? 0.80 : 0.62);   // (calibrated on coif5; shorter filters are not FP64-bound)
     const double m = bytes / 22.5 / 0.85;         // HBM fair share per SM per clock at 6.55 TB/s, 1.965 GHz
     const double fixed = 3000.0 + 700.0 * nf;     // load latency, barriers, drain: hidden only across resident CTAs
     const double time = std::max(std::max(c, m), (c + m + fixed) / (double)ctas);
