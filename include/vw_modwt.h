@@ -217,6 +217,19 @@ VW_API int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w
 /* halo length the two calls above require */
 VW_API int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels);
 
+/* ---- blockwise (streaming) batch analysis with carried left history ---------------------------------- */
+/* One level of BatchStreamingMODWT.processSingleLevel / processMultiLevel / flush*
+ * (EXT/extensions/modwt/BatchStreamingMODWT.java:55-163,183-276) on the history kernel's semantics
+ * (EXT/extensions/modwt/BatchSIMDMODWT.java:447-507): every row of vin is [history | block], where history holds the
+ * `hist` >= (l-1)*2^(level-1) samples of THIS level's input that precede the block (oldest first; the host fills it
+ * with zeros, the symmetric reflection of the first block, or the tail of the previous block) and block has n samples:
+ *   V[b][t] = sum_k hs[k] * ext[b][hist + t - k*2^(level-1)],  W likewise with gs,   t in [0, n).
+ * vin: [batch] rows of hist + n samples, row stride ldin; w, v: [batch][n] with strides ldw, ldv.  v may point into
+ * the next level's [history | block] buffer (the cascade then needs no copy).  Device pointers only. */
+VW_API int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t ldin, int64_t hist, int64_t n,
+                          const double *hs, const double *gs, int32_t l, int32_t level, double *w, int64_t ldw,
+                          double *v, int64_t ldv, uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

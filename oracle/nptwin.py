@@ -171,3 +171,52 @@ def universal_threshold(w1):
     n = a.size
     med = (a[n // 2 - 1] + a[n // 2]) / 2.0 if n % 2 == 0 else a[n // 2]
     return (med / 0.6745) * math.sqrt(2 * math.log(n))
+
+
+# ---- streaming (blockwise) batch analysis with carried history ------------------------------------------------------
+class StreamingOracle:
+    """Restates EXT/extensions/modwt/BatchStreamingMODWT.java:55-163,183-276 (+ history kernel
+    BatchSIMDMODWT.java:447-507) for ZERO_PADDING / SYMMETRIC: per level a left history of L_j - 1 samples of the
+    level's input; first block: zeros / symmetricBoundaryExtension of the block itself (:326-334); afterwards the
+    last L_j - 1 samples of [history | block] (:336-350).  Blocks are [B][n] (AoS)."""
+
+    def __init__(self, h, g, levels, mode):
+        self.levels, self.mode = levels, mode
+        self.low = [np.zeros((len(h) - 1) * (1 << j) + 1) for j in range(levels)]
+        self.high = [np.zeros((len(h) - 1) * (1 << j) + 1) for j in range(levels)]
+        for j in range(levels):   # ScalarOps.upsampleAndScaleForIMODWTSynthesis :909-916
+            self.low[j][::1 << j] = np.asarray(h) * S
+            self.high[j][::1 << j] = np.asarray(g) * S
+        self.hist = [None] * levels
+
+    def _level(self, j, cur, update=True):
+        b, n = cur.shape
+        hl = self.low[j].size - 1
+        if self.hist[j] is None:
+            if self.mode == 1:
+                self.hist[j] = np.zeros((b, hl))
+            else:
+                self.hist[j] = cur[:, mirror(np.arange(hl) - hl, n)]
+        ext = np.concatenate([self.hist[j], cur], axis=1)
+        a = np.zeros((b, n))
+        d = np.zeros((b, n))
+        for l in range(hl + 1):    # ascending taps, separate multiply and add, zeros of the dense filter included
+            s = ext[:, hl - l:hl - l + n]
+            a = a + s * self.low[j][l]
+            d = d + s * self.high[j][l]
+        if update:
+            self.hist[j] = ext[:, n:n + hl].copy()
+        return a, d
+
+    def process(self, block, update=True):
+        cur = np.asarray(block, dtype=np.float64)
+        ws = []
+        for j in range(self.levels):
+            cur, d = self._level(j, cur, update)
+            ws.append(d)
+        return np.stack(ws), cur
+
+    def flush(self, tail_length):
+        h0 = self.hist[0]
+        tail = np.zeros((h0.shape[0], tail_length)) if self.mode == 1 else h0[:, ::-1][:, :tail_length]
+        return self.process(tail, update=False)

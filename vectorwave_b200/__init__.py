@@ -11,5 +11,6 @@ from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentExcepti
 from .modwt import (MODWTResult, MODWTTransform, MultiLevelMODWTResult, MultiLevelMODWTTransform,  # noqa: F401
                     MutableMultiLevelMODWTResult, SymmetricAlignmentStrategy)
 from .ops import WaveletOperations  # noqa: F401
+from .streaming import BatchStreamingMODWT  # noqa: F401
 from .swt import VectorWaveSwtAdapter  # noqa: F401
 from .wavelets import BoundaryMode, Coiflet, Daubechies, Haar, Symlet, Wavelet, get_wavelet  # noqa: F401

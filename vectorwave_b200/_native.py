@@ -80,6 +80,7 @@ SIGNATURES = {
     "vw_swt_denoise": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, C.POINTER(VwAlign), _i32,
                                  C.c_double, _i32, _vp, _i64, _dp, _u32]),
     "vw_energy": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
+    "vw_modwt_stream_level": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _vp, _i64, _vp, _i64, _u32]),
     "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
     "vw_modwt_inverse_span": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _i32, _vp, _u32]),
     "vw_span_halo": (_i64, [_i32, _i32, _i32]),
@@ -421,6 +422,20 @@ class Engine:
                 gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), _vp(w.data_ptr()), w.stride(0),
                 _vp(v.data_ptr()), fl))
         return w, v
+
+    def stream_level(self, ext, hist, hs, gs, level, w_out, v_out, flags=0):
+        """One level of a streaming block: ext [B][hist + n] CUDA rows of [history | block] -> W, V [B][n] written into
+        w_out / v_out (2-D CUDA views, unit inner stride; v_out may be the block part of the next level's ext)."""
+        b, n = ext.shape[0], ext.shape[1] - hist
+        hs, gs = _fp(hs), _fp(gs)
+        assert ext.stride(1) == 1 and w_out.stride(1) == 1 and v_out.stride(1) == 1
+        fl = self._bind_stream(ext, w_out, v_out) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_stream_level(
+                self.ctx, _vp(ext.data_ptr()), int(b), ext.stride(0), int(hist), int(n), hs.ctypes.data_as(_dp),
+                gs.ctypes.data_as(_dp), hs.size, int(level), _vp(w_out.data_ptr()), w_out.stride(0),
+                _vp(v_out.data_ptr()), v_out.stride(0), fl))
+        return w_out, v_out
 
     def inverse_span(self, vin_ext, w_ext, halo, hs, gs, first_level, nlevels, order=ORDER_SPLIT, flags=0, out=None):
         """vin_ext [span | halo], w_ext [nlevels][span | halo] (CUDA) -> V_{first-1} [n_local]."""

@@ -774,6 +774,44 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
     return finish(ctx, flags, false);
 }
 
+int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t ldin, int64_t hist, int64_t n,
+                          const double *hs, const double *gs, int32_t l, int32_t level, double *w, int64_t ldw,
+                          double *v, int64_t ldv, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "streaming calls take device pointers only");
+    if (!vin || !w || !v) return vw_fail(ctx, VW_ENULL, "stream buffers cannot be null");
+    if (batch < 1) return vw_fail(ctx, VW_ELENGTH, "block must be non-null (batch=%lld)", (long long)batch);
+    if (n < 1) return vw_fail(ctx, VW_EEMPTY, "block length must be > 0");
+    if (level < 1 || level > 30) return vw_fail(ctx, VW_ELEVEL, "Invalid level: %d", level);
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    const int64_t d = (int64_t)1 << (level - 1);
+    const int64_t need = (int64_t)(l - 1) * d;
+    if (hist < need) return vw_fail(ctx, VW_ELENGTH, "history %lld shorter than the %lld samples level %d needs",
+                                    (long long)hist, (long long)need, level);
+    const int64_t n_in = hist + n;
+    if (ldin < n_in || ldw < n || ldv < n) return vw_fail(ctx, VW_ELENGTH, "row stride shorter than the row");
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    rc = VW_EUNSUPPORTED;
+    if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
+        // the [history | block] row is a linear span: the tile kernel (any dilation whose halo fits) or, for deep
+        // levels, the column kernel -- the same kernels as the whole-signal path
+        VwFusedFwd p{vin, ldin, w, ldw, 0, v, ldv, batch, n_in, hist, n, l, level, 1, VW_MODE_LINEAR, 0};
+        rc = vw_fused_forward(ctx, p, f);
+        if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+        if (rc == VW_EUNSUPPORTED && d >= 4 && ctx->opt_poly != 0) {
+            rc = vw_column_analysis(ctx, vin, ldin, v, ldv, w, ldw, n_in, hist, n, batch, f, l, d, VW_MODE_LINEAR);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+        }
+    }
+    if (rc == VW_EUNSUPPORTED)
+        rc = vw_launch_analysis_level(ctx, vin, ldin, v, ldv, w, ldw, n_in, hist, n, batch, f, l, d, VW_MODE_LINEAR, exact);
+    if (rc) return rc;
+    return finish(ctx, flags, false);
+}
+
 int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64_t level_stride_w, int64_t halo,
                           int64_t n_local, const double *hs, const double *gs, int32_t l, int32_t first_level,
                           int32_t nlevels, int32_t order, double *vout, uint32_t flags) {
