@@ -78,10 +78,10 @@ __device__ __forceinline__ double *row_ptr(char *base, int d, int r) {
 }
 
 // ---- analysis ------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool QMF>
 __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysis(const __grid_constant__ ColArgs a) {
     constexpr int R = col_rows<L>::value;
-    constexpr bool ST = col_smem_taps<L>::value;
+    constexpr bool ST = col_smem_taps<L>::value && !QMF;   // quadrature-mirror pairs fit the uniform registers: no LDS taps
     __shared__ double2 s_taps[ST ? L : 1];
     if (ST) {
         if (threadIdx.x < L) s_taps[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const int k = r - m;
-                        if (k >= 0 && k < L) { ah[r] = fma(a.f.h[k], xv, ah[r]); ag[r] = fma(a.f.g[k], xv, ag[r]); }
+                        if (k >= 0 && k < L) { ah[r] = fma(a.f.h[k], xv, ah[r]); ag[r] = fma(vw_tap_g<L, QMF>(a.f, k), xv, ag[r]); }
                     }
                 }
             }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
 // registers): input row m adds th[k] V_m + tg[k] W_m to output m-k; an output is complete after input row o+L-1.
 // A chunk of `nout` output rows consumes nout + L-1 input rows; block i reads input rows [iR, iR+R) and completes
 // output rows [iR-(L-1), iR-(L-1)+R).
-template <int L, bool EDGE>
+template <int L, bool EDGE, bool QMF>
 __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *__restrict__ v, const double *__restrict__ w,
                                                 char *op, int d, int nout, long long pin, uint32_t taps_addr, bool thr_on,
                                                 double lam) {
@@ -230,7 +230,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
 #pragma unroll
         for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = thr_on ? vw_threshold_value(nw[r], lam, a.thr_soft) : nw[r]; }
         if (in_left > R) load_block(R, in_left - R, nv, nw);
-        if (col_smem_taps_syn<L>::value) {
+        if (col_smem_taps_syn<L>::value && !QMF) {
 #pragma unroll
             for (int k = 0; k < L; k++) {
                 double hk, gk;
@@ -249,7 +249,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
                 for (int k = 0; k < L; k++) {
                     const int j = r + L - 1 - k;
                     acc[j] = fma(a.f.h[k], cv[r], acc[j]);
-                    acc[j] = fma(a.f.g[k], cw[r], acc[j]);
+                    acc[j] = fma(vw_tap_g<L, QMF>(a.f, k), cw[r], acc[j]);
                 }
             }
         }
@@ -276,9 +276,9 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
     }
 }
 
-template <int L>
+template <int L, bool QMF>
 __global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)) k_column_synthesis(const __grid_constant__ ColArgs a) {
-    constexpr bool ST = col_smem_taps_syn<L>::value;
+    constexpr bool ST = col_smem_taps_syn<L>::value && !QMF;
     __shared__ double2 s_taps[ST ? L : 1];
     if (ST) {
         if (threadIdx.x < L) s_taps[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
@@ -305,24 +305,25 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)
         const long long last_pos = pin0 + (long long)(nout + L - 2) * a.d;
         const bool thr_on = a.thr != nullptr && w != nullptr;
         const double lam = thr_on ? a.thr[a.thr_per_row ? b : 0] : 0.0;
-        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
-        else col_synth_chunk<L, true>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
+        if (pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in) col_synth_chunk<L, false, QMF>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
+        else col_synth_chunk<L, true, QMF>(a, v, w, op, d, nout, pin0, taps_addr, thr_on, lam);
     }
 }
 
-#define VW_DISPATCH_CL(L, CALL)           \
-    switch (L) {                          \
-        case 2: CALL(2); break;           \
-        case 4: CALL(4); break;           \
-        case 6: CALL(6); break;           \
-        case 8: CALL(8); break;           \
-        case 10: CALL(10); break;         \
-        case 12: CALL(12); break;         \
-        case 16: CALL(16); break;         \
-        case 18: CALL(18); break;         \
-        case 20: CALL(20); break;         \
-        case 30: CALL(30); break;         \
-        default: return VW_EUNSUPPORTED;  \
+// short filters keep both tap arrays in uniform registers; from 12 taps on a quadrature-mirror pair takes the QMF build
+#define VW_DISPATCH_CL(L, Q, CALL)                                  \
+    switch (L) {                                                    \
+        case 2: CALL(2, false); break;                              \
+        case 4: CALL(4, false); break;                              \
+        case 6: CALL(6, false); break;                              \
+        case 8: CALL(8, false); break;                              \
+        case 10: CALL(10, false); break;                            \
+        case 12: if (Q) CALL(12, true); else CALL(12, false); break; \
+        case 16: if (Q) CALL(16, true); else CALL(16, false); break; \
+        case 18: if (Q) CALL(18, true); else CALL(18, false); break; \
+        case 20: if (Q) CALL(20, true); else CALL(20, false); break; \
+        case 30: if (Q) CALL(30, true); else CALL(30, false); break; \
+        default: return VW_EUNSUPPORTED;                            \
     }
 
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &grid, int &rows_per_chunk, int &chunks_out) {
@@ -364,8 +365,9 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.off_h = a.off_g = 0;
     a.mode = mode;
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < l ? f.h[k] : 0.0; a.f.g[k] = k < l ? f.g[k] : 0.0; }
-#define VW_CA(LL) k_column_analysis<LL><<<grid, kCThreads, 0, ctx->stream>>>(a)
-    VW_DISPATCH_CL(l, VW_CA)
+    const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);
+#define VW_CA(LL, QQ) k_column_analysis<LL, QQ><<<grid, kCThreads, 0, ctx->stream>>>(a)
+    VW_DISPATCH_CL(l, qmf, VW_CA)
 #undef VW_CA
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column analysis launch");
@@ -390,8 +392,9 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
         a.f.h[k] = k < l ? (al.sigma_h > 0 ? f.h[k] : f.h[l - 1 - k]) : 0.0;
         a.f.g[k] = k < l ? (al.sigma_g > 0 ? f.g[k] : f.g[l - 1 - k]) : 0.0;
     }
-#define VW_CS(LL) k_column_synthesis<LL><<<grid, kCThreads, 0, ctx->stream>>>(a)
-    VW_DISPATCH_CL(l, VW_CS)
+    const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);   // on the arrays as the kernel sees them (sigma = -1 streams are reversed)
+#define VW_CS(LL, QQ) k_column_synthesis<LL, QQ><<<grid, kCThreads, 0, ctx->stream>>>(a)
+    VW_DISPATCH_CL(l, qmf, VW_CS)
 #undef VW_CS
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis launch");

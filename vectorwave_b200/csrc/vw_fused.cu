@@ -127,7 +127,7 @@ __device__ __forceinline__ void stage_tile(double *dst, const double *__restrict
 // analysis: out[i_r] = sum_k f[k] * in[i_r - k*d],  i_r = base + r*d.  One load feeds up to min(R,L) outputs x 2
 // filters.  `top` points at in[base + (R-1)*d]; the window is walked downwards with one pointer step per load.
 // FULL == false: only the first `nvalid` outputs exist; loads that would only feed the others are skipped.
-template <int L, int R, bool WITH_G, bool FULL>
+template <int L, int R, bool WITH_G, bool FULL, bool QMF>
 __device__ __forceinline__ void analysis_item(const double *__restrict__ top, int d, int nvalid, const VwFilt32 &f,
                                               double (&ah)[R], double (&ag)[R]) {
 #pragma unroll
@@ -144,16 +144,16 @@ __device__ __forceinline__ void analysis_item(const double *__restrict__ top, in
             const int k = r - m;
             if (k >= 0 && k < L) {
                 ah[r] = fma(f.h[k], xv, ah[r]);
-                if (WITH_G) ag[r] = fma(f.g[k], xv, ag[r]);
+                if (WITH_G) ag[r] = fma(vw_tap_g<L, QMF>(f, k), xv, ag[r]);
             }
         }
     }
 }
 
-// synthesis: acc[i_r] += sum_k taps[k] * in[i_r + k*d]; `bot` points at in[base]
-template <int L, int R, bool FULL>
-__device__ __forceinline__ void synthesis_item(const double *__restrict__ bot, int d, int nvalid,
-                                               const double (&taps)[VW_FUSED_MAX_L], double (&acc)[R]) {
+// synthesis: acc[i_r] += sum_k taps[k] * in[i_r + k*d]; `bot` points at in[base]; G selects the high-pass taps
+template <int L, int R, bool FULL, bool G, bool QMF>
+__device__ __forceinline__ void synthesis_item(const double *__restrict__ bot, int d, int nvalid, const VwFilt32 &f,
+                                               double (&acc)[R]) {
     const double *p = bot;
 #pragma unroll
     for (int m = 0; m <= R + L - 2; m++) {  // ascending m => ascending tap index per output
@@ -164,7 +164,7 @@ __device__ __forceinline__ void synthesis_item(const double *__restrict__ bot, i
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k = m - r;
-            if (k >= 0 && k < L) acc[r] = fma(taps[k], xv, acc[r]);
+            if (k >= 0 && k < L) acc[r] = fma(G ? vw_tap_g<L, QMF>(f, k) : f.h[k], xv, acc[r]);
         }
     }
 }
@@ -305,12 +305,12 @@ struct InvArgs {
 // fused analysis
 // ------------------------------------------------------------------------------------------------
 // shared memory: [tap pairs: 512 B][bufA: P][bufB: P][S0: T][S1: T] doubles (S only when use_stage), then one mbarrier
-template <int L>
+template <int L, bool QMF>
 __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_analysis(const __grid_constant__ FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;  // runtime filter length
     const int T = a.tile, HT = a.htot, P = T + HT;
-    constexpr bool ST = smem_taps<L>::value;
+    constexpr bool ST = smem_taps<L>::value && !QMF;   // a quadrature-mirror pair fits the uniform registers
     const uint32_t taps = smem_u32(smem_raw);
     if (ST && threadIdx.x < L) reinterpret_cast<double2 *>(smem_raw)[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
     double *buf0 = reinterpret_cast<double *>(smem_raw + kTapBytes);
@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                             else analysis_item_st<LL, kR, true, false>(top, d, nvalid, taps, ah, ag);
                         }
                     } else if (part == 0) {
-                        if (full) analysis_item<LL, kR, false, true>(top, d, nvalid, a.f, ah, ag);
-                        else analysis_item<LL, kR, false, false>(top, d, nvalid, a.f, ah, ag);
+                        if (full) analysis_item<LL, kR, false, true, QMF>(top, d, nvalid, a.f, ah, ag);
+                        else analysis_item<LL, kR, false, false, QMF>(top, d, nvalid, a.f, ah, ag);
                     } else {
-                        if (full) analysis_item<LL, kR, true, true>(top, d, nvalid, a.f, ah, ag);
-                        else analysis_item<LL, kR, true, false>(top, d, nvalid, a.f, ah, ag);
+                        if (full) analysis_item<LL, kR, true, true, QMF>(top, d, nvalid, a.f, ah, ag);
+                        else analysis_item<LL, kR, true, false, QMF>(top, d, nvalid, a.f, ah, ag);
                     }
                 } else {
                     if (part == 0) analysis_item_dyn<kR, false>(cur, base, d, PP - 1, LR, a.f, ah, ag);
@@ -452,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
 // fused synthesis (index rule t + k*d: PERIODIC, ZERO_PADDING, linear span)
 // ------------------------------------------------------------------------------------------------
 // shared memory: [tap pairs: 512 B][bufA: P][bufB: P][W0: P][W1: P] doubles, then three mbarriers (V, W0, W1)
-template <int L>
+template <int L, bool QMF>
 __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_synthesis(const __grid_constant__ InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int LR = L > 0 ? L : a.lrt;
     const int T = a.tile, HT = a.htot, P = T + HT;
-    constexpr bool ST = smem_taps<L>::value;
+    constexpr bool ST = smem_taps<L>::value && !QMF;   // a quadrature-mirror pair fits the uniform registers
     const uint32_t taps = smem_u32(smem_raw);
     if (ST && threadIdx.x < L) reinterpret_cast<double2 *>(smem_raw)[threadIdx.x] = make_double2(a.f.h[threadIdx.x], a.f.g[threadIdx.x]);
     double *buf0 = reinterpret_cast<double *>(smem_raw + kTapBytes);
@@ -546,11 +546,11 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                         else synthesis_item_st<LL, kR, false, false>(cv + base, wt + base, d, nvalid, taps, acc);
                     }
                 } else if (full) {
-                    synthesis_item<LL, kR, true>(cv + base, d, nvalid, a.f.h, acc);
-                    if (have_w) synthesis_item<LL, kR, true>(wt + base, d, nvalid, a.f.g, acc);
+                    synthesis_item<LL, kR, true, false, QMF>(cv + base, d, nvalid, a.f, acc);
+                    if (have_w) synthesis_item<LL, kR, true, true, QMF>(wt + base, d, nvalid, a.f, acc);
                 } else {
-                    synthesis_item<LL, kR, false>(cv + base, d, nvalid, a.f.h, acc);
-                    if (have_w) synthesis_item<LL, kR, false>(wt + base, d, nvalid, a.f.g, acc);
+                    synthesis_item<LL, kR, false, false, QMF>(cv + base, d, nvalid, a.f, acc);
+                    if (have_w) synthesis_item<LL, kR, false, true, QMF>(wt + base, d, nvalid, a.f, acc);
                 }
             } else {
                 synthesis_item_dyn<kR>(cv, base, d, in_ext - 1, LR, a.f.h, acc);
@@ -589,19 +589,20 @@ int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
                          "cudaFuncSetAttribute(max dynamic smem)");
 }
 
-#define VW_DISPATCH_L(L, CALL)            \
-    switch (L) {                          \
-        case 2: CALL(2); break;           \
-        case 4: CALL(4); break;           \
-        case 6: CALL(6); break;           \
-        case 8: CALL(8); break;           \
-        case 10: CALL(10); break;         \
-        case 12: CALL(12); break;         \
-        case 16: CALL(16); break;         \
-        case 18: CALL(18); break;         \
-        case 20: CALL(20); break;         \
-        case 30: CALL(30); break;         \
-        default: CALL(0); break;          \
+// from 16 taps on a quadrature-mirror pair (every orthogonal wavelet) takes the uniform-register QMF build
+#define VW_DISPATCH_L(L, Q, CALL)                                     \
+    switch (L) {                                                      \
+        case 2: CALL(2, false); break;                                \
+        case 4: CALL(4, false); break;                                \
+        case 6: CALL(6, false); break;                                \
+        case 8: CALL(8, false); break;                                \
+        case 10: CALL(10, false); break;                              \
+        case 12: CALL(12, false); break;                              \
+        case 16: if (Q) CALL(16, true); else CALL(16, false); break;  \
+        case 18: if (Q) CALL(18, true); else CALL(18, false); break;  \
+        case 20: if (Q) CALL(20, true); else CALL(20, false); break;  \
+        case 30: if (Q) CALL(30, true); else CALL(30, false); break;  \
+        default: CALL(0, false); break;                               \
     }
 
 }  // namespace
@@ -760,12 +761,13 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
     const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
     int rc = VW_OK;
-#define VW_FWD_CALL(LL)                                                                    \
+    const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);
+#define VW_FWD_CALL(LL, QQ)                                                                \
     do {                                                                                   \
-        if ((rc = set_smem(ctx, k_fused_analysis<LL>, smem))) return rc;                   \
-        k_fused_analysis<LL><<<grid, nthreads, smem, ctx->stream>>>(a);                    \
+        if ((rc = set_smem(ctx, k_fused_analysis<LL, QQ>, smem))) return rc;               \
+        k_fused_analysis<LL, QQ><<<grid, nthreads, smem, ctx->stream>>>(a);                \
     } while (0)
-    VW_DISPATCH_L(p.l, VW_FWD_CALL)
+    VW_DISPATCH_L(p.l, qmf, VW_FWD_CALL)
 #undef VW_FWD_CALL
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "fused analysis launch");
@@ -819,12 +821,13 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
     const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
     int rc = VW_OK;
-#define VW_INV_CALL(LL)                                                                    \
+    const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);   // on the arrays as the kernel sees them (reversed streams differ)
+#define VW_INV_CALL(LL, QQ)                                                                \
     do {                                                                                   \
-        if ((rc = set_smem(ctx, k_fused_synthesis<LL>, smem))) return rc;                  \
-        k_fused_synthesis<LL><<<grid, nthreads, smem, ctx->stream>>>(a);                   \
+        if ((rc = set_smem(ctx, k_fused_synthesis<LL, QQ>, smem))) return rc;              \
+        k_fused_synthesis<LL, QQ><<<grid, nthreads, smem, ctx->stream>>>(a);               \
     } while (0)
-    VW_DISPATCH_L(p.l, VW_INV_CALL)
+    VW_DISPATCH_L(p.l, qmf, VW_INV_CALL)
 #undef VW_INV_CALL
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "fused synthesis launch");

@@ -23,7 +23,23 @@ struct VwFilt32 {
     double h[VW_FUSED_MAX_L];
     double g[VW_FUSED_MAX_L];
 };
+#ifdef __CUDACC__
+// high-pass tap k with compile-time k: f.g[k], or +-f.h[L-1-k] when the pair is a quadrature mirror
+template <int L, bool QMF>
+__device__ __forceinline__ double vw_tap_g(const VwFilt32 &f, int k) {
+    return QMF ? ((k & 1) ? -f.h[L - 1 - k] : f.h[L - 1 - k]) : f.g[k];
+}
+#endif
 
+// Orthogonal wavelets: g[k] = (-1)^k h[L-1-k] (quadrature mirror, CORE/api/Daubechies.java:323-330 and the Symlet /
+// Coiflet twins); scaling by 1/sqrt(2) keeps the relation bit-exact.  When it holds, kernels for long filters read
+// only the L low-pass taps -- 2L doubles no longer fit the 63 uniform registers of an SM sub-partition, L do -- and
+// negate on the fly (free operand modifier).  Anything else (biorthogonal pairs, reversed streams) keeps both arrays.
+inline bool vw_is_qmf(const double *h, const double *g, int l) {
+    for (int k = 0; k < l; k++)
+        if (g[k] != ((k & 1) ? -h[l - 1 - k] : h[l - 1 - k])) return false;
+    return true;
+}
 struct vw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
