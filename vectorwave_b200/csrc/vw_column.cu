@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)
     }
 
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &grid, int &rows_per_chunk, int &chunks_out) {
-    if (d < 4 || d > (1ll << 30)) return VW_EUNSUPPORTED;   // below 4 a warp row access no longer covers whole sectors
+    if (d < 1 || d > (1ll << 30)) return VW_EUNSUPPORTED;
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
     // L-1 warm-up rows each chunk re-reads
@@ -349,7 +349,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &g
 }  // namespace
 
 int vw_column_min_level(const vw_ctx *ctx, int l) {
-    if (ctx->opt_colmin > 0) return (int)(ctx->opt_colmin < 3 ? 3 : ctx->opt_colmin);
+    if (ctx->opt_colmin > 0) return (int)ctx->opt_colmin;
     return l >= 24 ? 3 : 6;
 }
 

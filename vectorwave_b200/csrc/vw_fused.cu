@@ -609,6 +609,14 @@ int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
 
 namespace {
 
+// Threads per CTA.  Long filters run register-heavy item loops (2 CTAs of 256 threads per SM at most): 128-thread CTAs
+// put 4 independent tiles on an SM instead, whose load / compute / store phases overlap far better (coif5 fused
+// levels: 1.76 -> 1.3 ms per level; sym8 / db8 +3..5 %); short filters keep 256.
+int launch_threads(const vw_ctx *ctx, int l) {
+    if (ctx->opt_threads > 0) return (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31;
+    return l >= 16 ? 128 : kThreads;
+}
+
 int64_t even_up(int64_t v) { return (v + 1) & ~1ll; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -619,7 +627,7 @@ size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
 double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t t) {
-    const int nthreads = ctx->opt_threads > 0 ? (int)ctx->opt_threads : kThreads;
+    const int nthreads = launch_threads(ctx, l);
     const int64_t d0 = 1ll << (first - 1);
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
@@ -695,7 +703,8 @@ double group_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t
 
 int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out) {
     out.clear();
-    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : 4;
+    // FP64-bound filters (l >= 24) gain nothing from sharing a launch -- the halo recompute only adds FMAs (measured on coif5)
+    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : 4);
     const double kGeneric = 60.0;  // per-level kernels: one thread per output through L1/L2
     std::vector<double> best(levels + 1, INFINITY);
     std::vector<VwPlanGroup> pick(levels + 1);
@@ -759,7 +768,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
+    const int nthreads = launch_threads(ctx, p.l);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);
 #define VW_FWD_CALL(LL, QQ)                                                                \
@@ -819,7 +828,7 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = ctx->opt_threads > 0 ? (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31 : kThreads;
+    const int nthreads = launch_threads(ctx, p.l);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);   // on the arrays as the kernel sees them (reversed streams differ)
 #define VW_INV_CALL(LL, QQ)                                                                \
