@@ -63,7 +63,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, n_total, levels, mode_value, groups_f, groups_i, ret):
+def _worker(rank, world, port, name, n_total, levels, mode_value, groups_f, groups_i, upfront, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -72,7 +72,7 @@ def _worker(rank, world, port, name, n_total, levels, mode_value, groups_f, grou
         nl = n_total // world
         mode = BoundaryMode(mode_value)
         sh = SpanShardedMODWT(get_wavelet(name), levels, nl, mode, engine=NumpySpanEngine(), groups_forward=groups_f,
-                              groups_inverse=groups_i)
+                              groups_inverse=groups_i, upfront=upfront)
         res = sh.forward(torch.from_numpy(x[rank * nl:(rank + 1) * nl].copy()))
         xr = sh.inverse(res, order=1 if mode == BoundaryMode.ZERO_PADDING else 0)
         # second inverse must give the same answer (the result object survives an inverse)
@@ -84,18 +84,19 @@ def _worker(rank, world, port, name, n_total, levels, mode_value, groups_f, grou
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("upfront", [True, False])     # one exchange per direction vs one per launch group
 @pytest.mark.parametrize("mode", [BoundaryMode.PERIODIC, BoundaryMode.ZERO_PADDING])
 @pytest.mark.parametrize("name,n_total,levels,gf,gi", [
     ("db4", 2048, 5, [(1, 3), (4, 2)], [(1, 2), (3, 2), (5, 1)]),
     ("haar", 1024, 6, [(1, 4), (5, 1), (6, 1)], [(1, 4), (5, 2)]),
     ("sym8", 4096, 4, None, None),     # groups from the engine's planner (vw_plan_query)
 ])
-def test_span_sharded_two_ranks_equals_unsharded(mode, name, n_total, levels, gf, gi):
+def test_span_sharded_two_ranks_equals_unsharded(mode, name, n_total, levels, gf, gi, upfront):
     world = 2
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, name, n_total, levels, mode.value, gf, gi, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, name, n_total, levels, mode.value, gf, gi, upfront, ret), nprocs=world, join=True)
     h, g, wid = filters(name)
     x = np.random.default_rng(5).standard_normal(n_total)
     wo, vo = cref.decompose(x, h, g, levels, mode.value)

@@ -1,11 +1,16 @@
 """Multi-GPU sharding of the MODWT path: one process per GPU (torch.distributed; NCCL over NVLink on the box).
 
 * Batches shard by signal: contiguous blocks of signals per rank, no data-path communication (`shard_batch`).
-* One long signal shards by contiguous span: rank r owns samples [r*N/P, (r+1)*N/P).  Before every fused launch
-  group the ranks exchange the group's dilated halo with their ring neighbours (send/recv, PERIODIC wrap between the
-  last and the first rank): analysis needs the last (L-1)*2^(first-1)*(2^nlev-1) samples of V_{first-1} of the LEFT
-  neighbour, synthesis the first samples of V and of each W_j of the RIGHT neighbour.  Messages are <= 119 KB
-  (coif5, level 10), i.e. latency bound: NCCL send/recv inside one batch_isend_irecv group per exchange.
+* One long signal shards by contiguous span: rank r owns samples [r*N/P, (r+1)*N/P).  Analysis needs a LEFT halo
+  (indices t - k*2^(j-1)), synthesis a RIGHT halo (t + k*2^(j-1)), ring-wrapped between the last and the first rank for
+  PERIODIC, zeros at the open ends for ZERO_PADDING.  Two schedules:
+    - up front (default whenever the total halo (L-1)*(2^J-1) fits the span): ONE exchange per direction -- the last
+      H samples of x from the left neighbour before the analysis, the first samples of V_J and of every W_j from the
+      right neighbour before the synthesis -- and every level is computed on a region that shrinks by its own halo
+      (redundant recompute of <= H samples per level: 0.02 % at 2^27 samples per rank).  No per-level synchronisation.
+    - per launch group (fallback when the span is shorter than the total halo): the group's dilated halo
+      (L-1)*2^(first-1)*(2^nlev-1) is exchanged before every group.
+  Messages are <= a few hundred KB, i.e. latency bound: NCCL send/recv inside one batch_isend_irecv group.
   The result equals the unsharded transform bit for bit of the same kernels (the reference's
   forwardChunked has no halo and is NOT the semantics implemented here).
 
@@ -54,7 +59,7 @@ class SpanShardedMODWT:
     """decompose / reconstruct of one long signal spread over the ranks of `group` (PERIODIC or ZERO_PADDING)."""
 
     def __init__(self, wavelet, levels, n_local, boundaryMode=BoundaryMode.PERIODIC, group=None, engine=None,
-                 rank=None, world=None, groups_forward=None, groups_inverse=None):
+                 rank=None, world=None, groups_forward=None, groups_inverse=None, upfront=None):
         if boundaryMode not in (BoundaryMode.PERIODIC, BoundaryMode.ZERO_PADDING):
             raise IllegalArgumentException("span sharding supports PERIODIC and ZERO_PADDING (SYMMETRIC synthesis is "
                                            "two-sided per level; shard those by signal instead)")
@@ -80,8 +85,18 @@ class SpanShardedMODWT:
         self.halo_i = [_even_up(self._halo(f, k)) for f, k in self.gi]
         if max(self.halo_f + self.halo_i) > self.n_local:
             raise IllegalArgumentException("a level group's halo exceeds the per-rank span; use fewer ranks or levels")
-        self.pad = _even_up(max(self.halo_i))
-        self.lead = _even_up(max(self.halo_f))
+        # up-front schedule: cumulative (even-rounded) halos.  rf[g] = left halo still needed AFTER forward group g
+        # (by the later groups); si[g] = right halo the inverse needs on the INPUTS of group g (its own + the lower groups')
+        self.rf = [sum(self.halo_f[g + 1:]) for g in range(len(self.gf))]
+        self.si_out = [sum(self.halo_i[:g]) for g in range(len(self.gi))]
+        self.si_in = [self.si_out[g] + self.halo_i[g] for g in range(len(self.gi))]
+        total_f, total_i = sum(self.halo_f), sum(self.halo_i)
+        self.upfront = (max(total_f, total_i) <= self.n_local) if upfront is None else bool(upfront)
+        if self.upfront and max(total_f, total_i) > self.n_local:
+            raise IllegalArgumentException("the total halo exceeds the per-rank span: use the per-group schedule")
+        self.pad = total_i if self.upfront else _even_up(max(self.halo_i))
+        self.lead = total_f if self.upfront else _even_up(max(self.halo_f))
+        self.lead_w = self.rf[0] if self.upfront else 0     # W rows carry the not-yet-final left part of each level
 
     def _eng(self):
         if self.engine is None:
@@ -118,11 +133,69 @@ class SpanShardedMODWT:
                 req.wait()
 
     # -- analysis -------------------------------------------------------------------------------------------
+    def _forward_upfront(self, x_local):
+        """One exchange of the total left halo, then every group on [-(halo still needed later), n)."""
+        n, dev = self.n_local, x_local.device
+        eng = self._eng()
+        lead, lw = self.lead, self.lead_w
+        wfull = torch.empty((self.levels, lw + n + self.pad), dtype=torch.float64, device=dev)
+        vstore = torch.empty(n + self.pad, dtype=torch.float64, device=dev)
+        bufs = [torch.empty(lead + n, dtype=torch.float64, device=dev) for _ in range(2)]
+        bufs[0][lead:].copy_(x_local)
+        if lead > 0:
+            self._exchange(bufs[0][n:].contiguous(), bufs[0][:lead], to_right=True)   # my last `lead` samples -> right neighbour
+        cur, have = 0, lead                        # bufs[cur][lead - have:] holds V_{first-1} on [-have, n)
+        for g, (first, nlev) in enumerate(self.gf):
+            keep = self.rf[g]                      # left halo the later groups still need
+            last = g + 1 == len(self.gf)
+            vout = vstore[:n] if last else bufs[cur ^ 1][lead - keep:]
+            eng.forward_span(bufs[cur][lead - have:], have - keep, self.hs, self.gs, first, nlev,
+                             w_out=wfull[first - 1:first - 1 + nlev, lw - keep:], v_out=vout)
+            cur ^= 1
+            have = keep
+        return SpanResult(wfull[:, lw:], vstore, n, self.pad)
+
+    def _inverse_upfront(self, result, order):
+        """One exchange of the right halos of V_J and of every W_j, then every group on [0, n + halo needed below)."""
+        n, dev = self.n_local, result.v.device
+        eng = self._eng()
+        w, vtop = result.w, result.v
+        ng = len(self.gi)
+        # message: my first si_in[top] samples of V_J, and for every group the first si_in[g] samples of its W rows
+        pieces = [vtop[:self.si_in[ng - 1]]]
+        for g in range(ng):
+            first, nlev = self.gi[g]
+            pieces += [w[first - 1 + i, :self.si_in[g]] for i in range(nlev)]
+        send = torch.cat(pieces).contiguous()
+        recv = torch.empty_like(send)
+        if send.numel() > 0:
+            self._exchange(send, recv, to_right=False)
+        at = self.si_in[ng - 1]
+        vtop[n:n + at].copy_(recv[:at])
+        for g in range(ng):
+            first, nlev = self.gi[g]
+            for i in range(nlev):
+                w[first - 1 + i, n:n + self.si_in[g]].copy_(recv[at:at + self.si_in[g]])
+                at += self.si_in[g]
+        work = [torch.empty(n + self.pad, dtype=torch.float64, device=dev) for _ in range(2)]
+        vext, cur, out = vtop, 0, None
+        for g in range(ng - 1, -1, -1):
+            first, nlev = self.gi[g]
+            s_in, s_out = self.si_in[g], self.si_out[g]
+            dst = torch.empty(n, dtype=torch.float64, device=dev) if g == 0 else work[cur][:n + s_out]
+            eng.inverse_span(vext[:n + s_in], w[first - 1:first - 1 + nlev, :n + s_in], s_in - s_out, self.hrs, self.grs,
+                             first, nlev, order, out=dst)
+            out, vext = dst, work[cur]
+            cur ^= 1
+        return out
+
     def forward(self, x_local):
         """x_local: this rank's [n_local] span (float64, on the engine's device) -> SpanResult."""
         n, dev = self.n_local, x_local.device
         if x_local.numel() != n:
             raise IllegalArgumentException(f"expected a span of {n} samples, got {x_local.numel()}")
+        if self.upfront:
+            return self._forward_upfront(x_local)
         eng = self._eng()
         w = torch.empty((self.levels, n + self.pad), dtype=torch.float64, device=dev)
         vstore = torch.empty(n + self.pad, dtype=torch.float64, device=dev)
@@ -147,6 +220,8 @@ class SpanShardedMODWT:
 
     # -- synthesis ------------------------------------------------------------------------------------------
     def inverse(self, result, order=ORDER_SPLIT):
+        if self.upfront:
+            return self._inverse_upfront(result, order)
         n, dev = self.n_local, result.v.device
         eng = self._eng()
         w, pad = result.w, result.pad
