@@ -724,7 +724,9 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
     const bool exact = flags & VW_FLAG_BITEXACT;
     const int64_t n_in = halo + n_local;
     rc = VW_EUNSUPPORTED;
-    if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
+    // same kernel choice as the unsharded path: a single level at or above the column threshold runs on the column kernel
+    const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0;
+    if (!exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
         VwFusedFwd p{vin, n_in, w, n_local, level_stride_w, vout, n_local, 1, n_in, halo, n_local,
                      l, first_level, nlevels, VW_MODE_LINEAR, 0};
         rc = vw_fused_forward(ctx, p, f);
@@ -830,7 +832,8 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
     const bool exact = flags & VW_FLAG_BITEXACT;
     const int64_t n_in = halo + n_local;
     rc = VW_EUNSUPPORTED;
-    if (!exact && !(flags & VW_FLAG_NO_FUSE)) {
+    const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0;
+    if (!exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
         VwFusedInv p{vin, n_in, w, n_in, level_stride_w, nlevels >= 64 ? ~0ull : ((1ull << nlevels) - 1), vout, n_local,
                      1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0, 0};
         rc = vw_fused_inverse(ctx, p, f);
