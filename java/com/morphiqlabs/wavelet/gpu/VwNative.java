@@ -65,6 +65,18 @@ public final class VwNative {
     static final MethodHandle vw_universal_threshold = h("vw_universal_threshold",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT));
 
+    static final MethodHandle vw_energy = h("vw_energy",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT));
+    static final MethodHandle vw_device_alloc = h("vw_device_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
+    static final MethodHandle vw_device_free = h("vw_device_free", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle vw_copy_h2d = h("vw_copy_h2d", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
+    static final MethodHandle vw_copy_d2h = h("vw_copy_d2h", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
+    /** int vw_modwt_stream_level(ctx, vin, batch, ldin, hist, n, hs, gs, l, level, w, ldw, v, ldv, flags) -- one level of
+     *  BatchStreamingMODWT.process* on device rows of [history | block] (BatchStreamingMODWT.java:55-163) */
+    static final MethodHandle vw_modwt_stream_level = h("vw_modwt_stream_level",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS,
+                    JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_INT));
+
     private VwNative() {}
 
     /** Page-locked host memory as a segment of {@code bytes} bytes (freed with {@link #freePinned}). */

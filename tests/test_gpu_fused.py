@@ -265,3 +265,38 @@ def test_span_sharded_class_single_rank_on_device(eng):
         np.testing.assert_allclose(res.approximation().cpu().numpy(), vo, rtol=0, atol=tol(x))
         xr = sh.inverse(res, order=1 if mode == vw.BoundaryMode.ZERO_PADDING else 0)
         np.testing.assert_allclose(xr.cpu().numpy(), cref.reconstruct(wo, vo, h, g, mode.value, wid), rtol=0, atol=tol(x))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("name,b,n,levels", [("db4", 3, 4096, 4), ("haar", 2, 10000, 9), ("sym8", 2, 40000, 8),
+                                             ("coif5", 1, 65536, 8), ("db4", 2, 12345, 5), ("db8", 2, 6002, 4)])
+def test_no_kernel_writes_outside_its_rows(eng, mode, name, b, n, levels):
+    """Out-of-bounds guard without a sanitizer (compute-sanitizer is not available on the pool): every output row sits
+    inside a larger sentinel-filled allocation (row stride n + 64, level stride with a gap, 64 guard samples in front);
+    after forward + inverse through the tile, column and per-level kernels the guard samples must be untouched."""
+    import torch
+    from vectorwave_b200.modwt import multilevel_alignment
+    h, g, wid = filters(name)
+    rng = np.random.default_rng(n + mode)
+    x = rng.standard_normal((b, n))
+    xd = torch.as_tensor(x, device="cuda")
+    ld, guard, sentinel = n + 64, 64, 1234.5
+    lsw = b * ld + 128
+    store = torch.full((guard + levels * lsw + b * ld + guard + b * ld + guard,), sentinel, dtype=torch.float64, device="cuda")
+    w = torch.as_strided(store, (levels, b, n), (lsw, ld, 1), guard)
+    v = torch.as_strided(store, (b, n), (ld, 1), guard + levels * lsw)
+    xr = torch.as_strided(store, (b, n), (ld, 1), guard + levels * lsw + b * ld + guard)
+    eng.forward(xd, h * S, g * S, levels, mode, 0, w, v)
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(vw.get_wavelet(name), bm, levels)
+    eng.inverse(w.contiguous(), v.contiguous(), h * S, g * S, mode, align, order, out=xr)
+    torch.cuda.synchronize()
+    mask = torch.ones_like(store, dtype=torch.bool)
+    for t in (w, v, xr):
+        torch.as_strided(mask, t.shape, t.stride(), t.storage_offset()).fill_(False)
+    assert bool((store[mask] == sentinel).all()), "a kernel wrote outside its output rows"
+    for i in range(b):
+        wo, vo = cref.decompose(x[i], h, g, levels, mode)
+        np.testing.assert_allclose(w[:, i, :].cpu().numpy(), wo, rtol=0, atol=tol(x))
+        np.testing.assert_allclose(v[i].cpu().numpy(), vo, rtol=0, atol=tol(x))
+        np.testing.assert_allclose(xr[i].cpu().numpy(), cref.reconstruct(wo, vo, h, g, mode, wid), rtol=0, atol=tol(x))
