@@ -193,6 +193,16 @@ VW_API int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n
                    const double *gs, int32_t l, int32_t levels, int32_t mode, const vw_align *align, int32_t order,
                    double threshold, int32_t soft, double *out, int64_t ldo, double *thresholds_out, uint32_t flags);
 
+/* WaveletDenoiser.estimateNoiseSigma's order statistic (CORE/denoising/WaveletDenoiser.java:376-387,587-597): the exact
+ * median of |c| per row (even count: mean of the two middle values).  sigma = median / 0.6745 stays on the host.
+ * out: `batch` doubles on the HOST. */
+VW_API int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags);
+
+/* Mean and population variance about the mean per row -- the two loops of WaveletDenoiser.calculateBayesThreshold
+ * (CORE/denoising/WaveletDenoiser.java:521-552).  mean_out, var_out: `batch` doubles each on the HOST. */
+VW_API int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out,
+                     double *var_out, uint32_t flags);
+
 /* sum of squares per row: MultiLevelMODWTResult.getDetailEnergyAtLevel / getApproximationEnergy
  * (CORE/modwt/MultiLevelMODWTResultImpl.java:91-139).  out: `batch` doubles on the HOST. */
 VW_API int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags);

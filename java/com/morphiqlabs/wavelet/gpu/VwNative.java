@@ -67,6 +67,10 @@ public final class VwNative {
 
     static final MethodHandle vw_energy = h("vw_energy",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT));
+    static final MethodHandle vw_median_abs = h("vw_median_abs",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT));
+    static final MethodHandle vw_mean_variance = h("vw_mean_variance",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT));
     static final MethodHandle vw_device_alloc = h("vw_device_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
     static final MethodHandle vw_device_free = h("vw_device_free", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle vw_copy_h2d = h("vw_copy_h2d", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));

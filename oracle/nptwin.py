@@ -220,3 +220,62 @@ class StreamingOracle:
         h0 = self.hist[0]
         tail = np.zeros((h0.shape[0], tail_length)) if self.mode == 1 else h0[:, ::-1][:, :tail_length]
         return self.process(tail, update=False)
+
+
+# ---- WaveletDenoiser (CORE/denoising/WaveletDenoiser.java) ------------------------------------------------------------
+def _seq_sum(a):
+    """Java's `for (double c : coeffs) s += c` -- sequential, not numpy's pairwise summation"""
+    s = 0.0
+    for c in np.asarray(a, dtype=np.float64):
+        s += float(c)
+    return s
+
+
+def denoiser_threshold(coeffs, sigma, method):
+    """calculateThreshold (:391-436) for UNIVERSAL / MINIMAX / BAYES"""
+    import math
+    n = len(coeffs)
+    if method == "UNIVERSAL":
+        return sigma * math.sqrt(2.0 * math.log(n))
+    if method == "MINIMAX":                                 # :497-509
+        log_n = math.log(n)
+        if n <= 32:
+            return 0.0
+        if n <= 64:
+            return sigma * 0.3936 + 0.1829 * sigma * log_n
+        return sigma * (0.4745 + 0.1148 * log_n)
+    if method == "BAYES":                                   # :521-552
+        sigma2 = sigma * sigma
+        mean = _seq_sum(coeffs) / n
+        variance = _seq_sum((np.asarray(coeffs) - mean) ** 2) / n
+        return sigma2 / math.sqrt(max(0.0, variance - sigma2) + 1e-10)
+    raise ValueError(method)
+
+
+def denoiser_sigma(detail):
+    """estimateNoiseSigma (:376-387) + calculateMedian (:587-597)"""
+    a = np.sort(np.abs(np.asarray(detail, dtype=np.float64)))
+    n = a.size
+    med = (a[n // 2 - 1] + a[n // 2]) / 2.0 if n % 2 == 0 else a[n // 2]
+    return med / 0.6745
+
+
+def denoiser_single(x, h, g, mode, method, soft, fixed=None):
+    """denoise (:124-145) / denoiseFixed (:354-366): single level, MODWTTransform.inverse (pair-added, SYMMETRIC t-l)"""
+    v, w = forward_single(x, h, g, mode)
+    thr = fixed if fixed is not None else denoiser_threshold(w, denoiser_sigma(w), method)
+    return inverse_single(v, threshold(w, thr, soft), h, g, mode), thr
+
+
+def denoiser_multilevel(x, h, g, levels, mode, wavelet_id, method, soft):
+    """denoiseMultiLevel (:155-171): sigma from level 1; level j thresholded with calculateThreshold(W_j, sigma/sqrt(2^j))"""
+    import math
+    w, v = decompose(x, h, g, levels, mode)
+    sigma = denoiser_sigma(w[0])
+    thrs = []
+    wd = np.empty_like(w)
+    for j in range(levels):
+        thr = denoiser_threshold(w[j], sigma / math.sqrt(1 << (j + 1)), method)
+        thrs.append(thr)
+        wd[j] = threshold(w[j], thr, soft)
+    return reconstruct(wd, v, h, g, mode, wavelet_id), thrs

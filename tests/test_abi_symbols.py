@@ -19,7 +19,7 @@ def _declared():
 def test_header_declares_the_expected_surface():
     names = _declared()
     for must in ("vw_init", "vw_modwt_forward", "vw_modwt_inverse", "vw_swt_denoise", "vw_conv_modwt",
-                 "vw_modwt_forward_span", "vw_modwt_inverse_span", "vw_modwt_stream_level", "vw_universal_threshold", "vw_threshold"):
+                 "vw_modwt_forward_span", "vw_modwt_inverse_span", "vw_modwt_stream_level", "vw_median_abs", "vw_mean_variance", "vw_universal_threshold", "vw_threshold"):
         assert must in names
     assert len(names) >= 25
 

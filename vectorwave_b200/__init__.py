@@ -6,6 +6,7 @@ tests and the benchmark, and the ctypes twin of the Java FFM binding in java/.
 """
 from ._native import Engine, load_library, LIB_PATH  # noqa: F401
 from .batch import BatchMODWT, BatchSIMDMODWT, MultiLevelResult, SingleLevelResult  # noqa: F401
+from .denoising import ThresholdMethod, ThresholdType, WaveletDenoiser  # noqa: F401
 from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentException, InvalidSignalException,  # noqa: F401
                      NativeEngineError, NullPointerException, WaveletTransformException)
 from .modwt import (MODWTResult, MODWTTransform, MultiLevelMODWTResult, MultiLevelMODWTTransform,  # noqa: F401

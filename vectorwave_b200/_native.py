@@ -80,6 +80,8 @@ SIGNATURES = {
     "vw_swt_denoise": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, C.POINTER(VwAlign), _i32,
                                  C.c_double, _i32, _vp, _i64, _dp, _u32]),
     "vw_energy": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
+    "vw_median_abs": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
+    "vw_mean_variance": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _u32]),
     "vw_modwt_stream_level": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _vp, _i64, _vp, _i64, _u32]),
     "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
     "vw_modwt_inverse_span": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _i32, _vp, _u32]),
@@ -392,6 +394,26 @@ class Engine:
                 int(levels), int(mode), al, int(order), float(threshold), int(bool(soft)), _vp(_ptr(res)), _ld(res),
                 thr.ctypes.data_as(_dp), fl))
         return (res[0], float(thr[0])) if one_d else (res, thr)
+
+    def median_abs(self, c, flags=0):
+        """exact median(|c|) per row (WaveletDenoiser.estimateNoiseSigma's order statistic)"""
+        c2, one_d = self._rows(c, "coefficients")
+        out = np.empty(c2.shape[0])
+        fl = self._bind_stream(c2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_median_abs(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
+                                               out.ctypes.data_as(_dp), fl))
+        return float(out[0]) if one_d else out
+
+    def mean_variance(self, c, flags=0):
+        """(mean, population variance about the mean) per row"""
+        c2, one_d = self._rows(c, "coefficients")
+        m, v = np.empty(c2.shape[0]), np.empty(c2.shape[0])
+        fl = self._bind_stream(c2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_mean_variance(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
+                                                  m.ctypes.data_as(_dp), v.ctypes.data_as(_dp), fl))
+        return (float(m[0]), float(v[0])) if one_d else (m, v)
 
     def energy(self, c, flags=0):
         c2, one_d = self._rows(c, "coefficients")

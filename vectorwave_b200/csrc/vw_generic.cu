@@ -151,6 +151,28 @@ __global__ void __launch_bounds__(512) k_energy(const double *__restrict__ c, in
     }
 }
 
+// one CTA per row: sum of (c - shift)^POW; deterministic tree.  shift = nullptr: 0
+template <int POW>
+__global__ void __launch_bounds__(512) k_row_moment(const double *__restrict__ c, int64_t n, int64_t ld, const double *shift,
+                                                    double scale, double *out) {
+    __shared__ double part[16];
+    const double *row = c + (int64_t)blockIdx.x * ld;
+    const double m = shift ? shift[blockIdx.x] : 0.0;
+    double s = 0.0;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const double x = row[t] - m;
+        s = POW == 1 ? s + x : fma(x, x, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = s * scale;
+    }
+}
+
 dim3 grid2d(int64_t n, int64_t batch) {
     return dim3((unsigned)((n + 255) / 256), (unsigned)(batch < 32768 ? batch : 32768));
 }
@@ -210,6 +232,16 @@ int vw_launch_nonfinite_count(vw_ctx *ctx, const double *x, int64_t batch, int64
     k_nonfinite_count<<<grid2d(n, batch), 256, 0, ctx->stream>>>(x, batch, n, ld, count_dev);
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "finite check launch");
+}
+
+int vw_launch_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_dev,
+                            double *var_dev) {
+    if (batch <= 0 || n <= 0) return VW_OK;
+    // mean = sum / n, then variance = sum (c - mean)^2 / n: the two loops of calculateBayesThreshold (:525-537)
+    k_row_moment<1><<<(unsigned)batch, 512, 0, ctx->stream>>>(c, n, ld, nullptr, 1.0 / (double)n, mean_dev);
+    k_row_moment<2><<<(unsigned)batch, 512, 0, ctx->stream>>>(c, n, ld, mean_dev, 1.0 / (double)n, var_dev);
+    ctx->launches += 2;
+    return vw_cuda_check(ctx, cudaGetLastError(), "mean/variance launch");
 }
 
 int vw_launch_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out_dev) {

@@ -135,3 +135,7 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
 // median(|w1|) per row -> universal thresholds written to thr_dev[batch] (device).
 int vw_launch_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld,
                                   double *thr_dev);
+// same selection, raw median(|c|) per row
+int vw_launch_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *med_dev);
+int vw_launch_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_dev,
+                            double *var_dev);

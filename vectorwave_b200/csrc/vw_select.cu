@@ -145,19 +145,31 @@ __global__ void k_select_mirror_count(SelState *st, int64_t batch) {   // same p
     if (st[b].prefix[0] == st[b].prefix[1]) st[b].count[1] = st[b].count[0];
 }
 
+// factor >= 0: universal threshold (median / 0.6745) * factor (0 for n = 1); factor < 0: the raw median
 __global__ void k_select_finish(const SelState *st, int64_t batch, int64_t n, double factor, double *thr) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     double lo = __longlong_as_double((long long)st[b].prefix[0]);
     double hi = __longlong_as_double((long long)st[b].prefix[1]);
     double med = (n % 2 == 0) ? __ddiv_rn(__dadd_rn(lo, hi), 2.0) : hi;
-    thr[b] = __dmul_rn(__ddiv_rn(med, 0.6745), factor);
+    thr[b] = factor >= 0.0 ? __dmul_rn(__ddiv_rn(med, 0.6745), factor) : med;
 }
 
 }  // namespace
 
+static int select_median(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld, double *thr_dev, double factor);
+
 int vw_launch_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld,
                                   double *thr_dev) {
+    // Math.sqrt(2 * Math.log(n)), CORE/swt/VectorWaveSwtAdapter.java:512
+    return select_median(ctx, w1, batch, n, ld, thr_dev, sqrt(2.0 * log((double)n)));
+}
+
+int vw_launch_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *med_dev) {
+    return select_median(ctx, c, batch, n, ld, med_dev, -1.0);
+}
+
+static int select_median(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld, double *thr_dev, double factor) {
     if (batch <= 0 || n <= 0) return VW_OK;
     void *ws = nullptr;
     int64_t cap64 = n / 64;
@@ -197,7 +209,6 @@ int vw_launch_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, 
         k_select_pick<8><<<(unsigned)(batch * 2), 256, 0, ctx->stream>>>(st, hist);
         ctx->launches += 2;
     }
-    double factor = sqrt(2.0 * log((double)n));  // Math.sqrt(2 * Math.log(n)), CORE/swt/VectorWaveSwtAdapter.java:512
     k_select_finish<<<nb, 128, 0, ctx->stream>>>(st, batch, n, factor, thr_dev);
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "universal threshold launch");

@@ -683,6 +683,52 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "denoise");
 }
 
+int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
+    if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
+    const double *cd = c;
+    int64_t ldd = ld;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, c, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+        cd = (const double *)p; ldd = n;
+    }
+    void *pt;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pt))) return rc;
+    double *med = (double *)((char *)pt + 64);
+    if ((rc = vw_launch_median_abs(ctx, cd, batch, n, ldd, med))) return rc;
+    cudaMemcpyAsync(out, med, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "median");
+}
+
+int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out, double *var_out,
+                     uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
+    if (!mean_out || !var_out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
+    const double *cd = c;
+    int64_t ldd = ld;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, c, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+        cd = (const double *)p; ldd = n;
+    }
+    void *pt;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 16 + 64, &pt))) return rc;
+    double *md = (double *)((char *)pt + 64), *vd = md + batch;
+    if ((rc = vw_launch_mean_variance(ctx, cd, batch, n, ldd, md, vd))) return rc;
+    cudaMemcpyAsync(mean_out, md, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(var_out, vd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "mean/variance");
+}
+
 int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx->device);

@@ -12,6 +12,7 @@ class ErrorCode(enum.Enum):
     VAL_TOO_LARGE = "VAL_005"
     VAL_EMPTY = "VAL_006"
     VAL_LENGTH_MISMATCH = "VAL_007"
+    CFG_UNSUPPORTED_OPERATION = "CFG_001"
     CFG_UNSUPPORTED_BOUNDARY_MODE = "CFG_003"
     CFG_INVALID_DECOMPOSITION_LEVEL = "CFG_004"
     STATE_INVALID = "STATE_002"
