@@ -300,3 +300,27 @@ def test_no_kernel_writes_outside_its_rows(eng, mode, name, b, n, levels):
         np.testing.assert_allclose(w[:, i, :].cpu().numpy(), wo, rtol=0, atol=tol(x))
         np.testing.assert_allclose(v[i].cpu().numpy(), vo, rtol=0, atol=tol(x))
         np.testing.assert_allclose(xr[i].cpu().numpy(), cref.reconstruct(wo, vo, h, g, mode, wid), rtol=0, atol=tol(x))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pipelined_host_path_equals_oracle(eng, mode):
+    """Host-buffer calls on large batches are chunked over two streams (H2D / kernels / D2H overlap).  Forced here on a
+    small batch via the pipe_min option: ragged last chunk, pinned and pageable buffers, every boundary mode."""
+    from vectorwave_b200.modwt import multilevel_alignment
+    eng.set_option("pipe_min", 1)
+    try:
+        rng = np.random.default_rng(21 + mode)
+        for name, b, n, levels in (("db4", 7, 3000, 4), ("sym8", 5, 8192, 6), ("haar", 2, 1001, 3)):
+            h, g, wid = filters(name)
+            x = rng.standard_normal((b, n))
+            xp = eng.pinned_empty((b, n))
+            xp[...] = x
+            for src in (x, xp):
+                w, v = _check_forward(eng, src, name, levels, mode, _native.FLAG_CHECK_FINITE)
+                _check_inverse(eng, w, v, name, mode, x)
+        bad = rng.standard_normal((6, 2000))
+        bad[4, 17] = np.nan                       # the finite check runs per chunk
+        with pytest.raises(vw.InvalidSignalException):
+            eng.forward(bad, *(filters("db4")[i] * S for i in (0, 1)), 3, mode, _native.FLAG_CHECK_FINITE)
+    finally:
+        eng.set_option("pipe_min", 64 << 20)

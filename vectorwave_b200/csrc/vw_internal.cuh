@@ -49,9 +49,12 @@ struct vw_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     // grow-only device scratch (ping-pong V buffers, staged host I/O, selection workspaces)
-    static const int kScratch = 6;
-    void *scratch[kScratch] = {};
-    size_t scratch_bytes[kScratch] = {};
+    static const int kScratch = 6;         // per set; set 1 belongs to the second stream of the pipelined host path
+    void *scratch[2 * kScratch] = {};
+    size_t scratch_bytes[2 * kScratch] = {};
+    int scratch_set = 0;
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // created on first use by the pipelined host path
+    int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;

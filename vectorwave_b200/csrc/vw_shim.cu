@@ -33,6 +33,7 @@ int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what) {
 
 int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
+    slot += ctx->scratch_set * vw_ctx::kScratch;
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
             cudaStreamSynchronize(ctx->stream);
@@ -282,6 +283,98 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
     return VW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// host-buffer calls on large batches: chunk the batch and alternate two streams, so the H2D copy of chunk c+1, the
+// kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex and the copy engines are separate;
+// the double[] API moves (levels + 2) * 8 bytes per sample each way, which is what bounds e2e throughput).
+// Every stream owns its own scratch set.  Signals are independent, so chunking by rows changes no result.
+// ------------------------------------------------------------------------------------------------
+struct PipeGuard {
+    vw_ctx *ctx;
+    cudaStream_t saved;
+    explicit PipeGuard(vw_ctx *c) : ctx(c), saved(c->stream) {}
+    ~PipeGuard() { ctx->stream = saved; ctx->scratch_set = 0; }
+};
+
+int pipe_streams(vw_ctx *ctx) {
+    for (int i = 0; i < 2; i++)
+        if (!ctx->pipe_stream[i]) {
+            int rc = vw_cuda_check(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking), "pipeline stream");
+            if (rc) return rc;
+        }
+    return VW_OK;
+}
+
+// rows per chunk: chunks of >= 16 MB staged bytes, at most 8 of them, at least 2
+int64_t pipe_rows(const vw_ctx *ctx, int64_t batch, int64_t n, int levels) {
+    const double total = (double)batch * (double)n * 8.0 * (levels + 2);
+    if (ctx->opt_pipe_min <= 0 || batch < 2 || total < (double)ctx->opt_pipe_min) return 0;
+    int64_t chunks = (int64_t)(total / (16.0 * 1048576.0));
+    chunks = std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(chunks, 8), batch));
+    return (batch + chunks - 1) / chunks;
+}
+
+int forward_host_pipelined(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const VwFilt &f, int l,
+                           int levels, int mode, double *w, int64_t ldw, int64_t lsw, double *vj, int64_t ldv, uint32_t flags,
+                           int64_t rows) {
+    int rc;
+    if ((rc = pipe_streams(ctx))) return rc;
+    if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize"))) return rc;
+    PipeGuard guard(ctx);
+    int c = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += rows, c++) {
+        const int64_t rb = std::min(rows, batch - b0);
+        ctx->scratch_set = c & 1;
+        ctx->stream = ctx->pipe_stream[c & 1];
+        void *px, *pw;
+        const size_t bn = (size_t)rb * (size_t)n;
+        if ((rc = vw_scratch(ctx, 2, (size_t)rows * (size_t)n * 8, &px))) return rc;
+        if ((rc = vw_scratch(ctx, 3, (size_t)rows * (size_t)n * 8 * (size_t)(levels + 1), &pw))) return rc;
+        double *xd = (double *)px, *wd = (double *)pw, *vd = wd + bn * (size_t)levels;
+        if ((rc = copy_rows(ctx, xd, n, x + b0 * ldx, ldx, n, rb, cudaMemcpyHostToDevice))) return rc;
+        if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, rb, n, n, "signal"))) return rc;
+        if ((rc = forward_device(ctx, xd, rb, n, n, f, l, levels, mode, wd, n, (int64_t)bn, vd, n, flags))) return rc;
+        for (int j = 0; j < levels; j++)
+            if ((rc = copy_rows(ctx, w + (int64_t)j * lsw + b0 * ldw, ldw, wd + (size_t)j * bn, n, n, rb, cudaMemcpyDeviceToHost))) return rc;
+        if ((rc = copy_rows(ctx, vj + b0 * ldv, ldv, vd, n, n, rb, cudaMemcpyDeviceToHost))) return rc;
+    }
+    for (int i = 0; i < 2; i++)
+        if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]), "pipeline synchronize"))) return rc;
+    return VW_OK;
+}
+
+int inverse_host_pipelined(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const double *vj, int64_t ldv,
+                           int64_t batch, int64_t n, const VwFilt &f, int l, int levels, int mode, const vw_align *align,
+                           int order, uint64_t detail_mask, int use_approx, double *xout, int64_t ldx, uint32_t flags,
+                           int64_t rows) {
+    int rc;
+    if ((rc = pipe_streams(ctx))) return rc;
+    if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize"))) return rc;
+    PipeGuard guard(ctx);
+    int c = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += rows, c++) {
+        const int64_t rb = std::min(rows, batch - b0);
+        ctx->scratch_set = c & 1;
+        ctx->stream = ctx->pipe_stream[c & 1];
+        void *px, *pw;
+        const size_t bn = (size_t)rb * (size_t)n;
+        if ((rc = vw_scratch(ctx, 2, (size_t)rows * (size_t)n * 8, &px))) return rc;
+        if ((rc = vw_scratch(ctx, 3, (size_t)rows * (size_t)n * 8 * (size_t)(levels + 1), &pw))) return rc;
+        double *xd = (double *)px, *wd = (double *)pw, *vd = wd + bn * (size_t)levels;
+        for (int j = 0; j < levels; j++)
+            if ((rc = copy_rows(ctx, wd + (size_t)j * bn, n, w + (int64_t)j * lsw + b0 * ldw, ldw, n, rb, cudaMemcpyHostToDevice))) return rc;
+        if ((rc = copy_rows(ctx, vd, n, vj + b0 * ldv, ldv, n, rb, cudaMemcpyHostToDevice))) return rc;
+        if (flags & VW_FLAG_CHECK_FINITE)
+            if ((rc = check_finite(ctx, wd, (int64_t)(levels + 1) * rb, n, n, "coefficients"))) return rc;
+        if ((rc = inverse_device(ctx, wd, n, (int64_t)bn, vd, n, rb, n, f, l, levels, mode, align, order, detail_mask,
+                                 use_approx, xd, n, flags, nullptr, 0, 0))) return rc;
+        if ((rc = copy_rows(ctx, xout + b0 * ldx, ldx, xd, n, n, rb, cudaMemcpyDeviceToHost))) return rc;
+    }
+    for (int i = 0; i < 2; i++)
+        if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]), "pipeline synchronize"))) return rc;
+    return VW_OK;
+}
+
 int check_signal_args(vw_ctx *ctx, const void *x, int64_t batch, int64_t n, int64_t ld) {
     if (!x) return vw_fail(ctx, VW_ENULL, "signal cannot be null");
     if (batch < 1) return vw_fail(ctx, VW_ELENGTH, "signals must be non-null and non-empty (batch=%lld)", (long long)batch);
@@ -343,7 +436,8 @@ int vw_destroy(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 2 * vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 2; i++) if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -379,6 +473,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "threads")) ctx->opt_threads = value;
     else if (!strcmp(name, "poly")) ctx->opt_poly = value;
     else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
+    else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
     return VW_OK;
 }
@@ -515,6 +610,8 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
         return finish(ctx, flags, false);
     }
     // host buffers: stage x -> device (packed rows), run, stage W and V_J back
+    if (const int64_t rows = pipe_rows(ctx, batch, n, levels))
+        return forward_host_pipelined(ctx, x, batch, n, ldx, f, l, levels, mode, w, ldw, level_stride_w, vj, ldv, flags, rows);
     void *px, *pw;
     size_t bn = (size_t)batch * (size_t)n;
     if ((rc = vw_scratch(ctx, 2, bn * 8, &px))) return rc;
@@ -563,6 +660,9 @@ int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_st
                                  detail_mask, use_approx, xout, ldx, flags, nullptr, 0, 0))) return rc;
         return finish(ctx, flags, false);
     }
+    if (const int64_t rows = pipe_rows(ctx, batch, n, levels))
+        return inverse_host_pipelined(ctx, w, ldw, level_stride_w, vj, ldv, batch, n, f, l, levels, mode, align, order,
+                                      detail_mask, use_approx, xout, ldx, flags, rows);
     void *px, *pw;
     size_t bn = (size_t)batch * (size_t)n;
     if ((rc = vw_scratch(ctx, 2, bn * 8, &px))) return rc;
