@@ -205,6 +205,17 @@ def test_batch_facade_matches_core():
     w_soa, v_soa = cref.batch_soa_decompose(soa, 4, 64, *filters("db2")[:2], 2)
     close(np.stack(d), w_soa, x)
     close(a, v_soa, x)
+    # the same statics on device-resident SoA buffers (transposes on the device, nothing crosses PCIe)
+    import torch
+    soa_d = torch.as_tensor(soa, device="cuda")
+    d_d = [torch.empty(256, dtype=torch.float64, device="cuda") for _ in range(2)]
+    a_d = torch.empty(256, dtype=torch.float64, device="cuda")
+    vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa_d, d_d, a_d, vw.Daubechies.DB2, 4, 64, 2)
+    close(np.stack([t.cpu().numpy() for t in d_d]), w_soa, x)
+    close(a_d.cpu().numpy(), v_soa, x)
+    s_a, s_d = torch.empty_like(a_d), torch.empty_like(a_d)
+    vw.BatchSIMDMODWT.batchMODWTSoA(soa_d, s_a, s_d, vw.Haar.INSTANCE if hasattr(vw.Haar, "INSTANCE") else vw.get_wavelet("haar"), 4, 64)
+    close(s_a.cpu().numpy().reshape(64, 4).T, np.stack([cref.forward_single(x[i], np.array([0.5, 0.5]) / nptwin.S, np.array([0.5, -0.5]) / nptwin.S, 0)[0] for i in range(4)]), x)
     with pytest.raises(vw.IllegalArgumentException):
         vw.BatchMODWT.multiLevelAoS(vw.Daubechies.DB4, x, 0)
     with pytest.raises(vw.IllegalArgumentException):
@@ -337,3 +348,22 @@ def test_error_behaviour():
     with pytest.raises(vw.InvalidArgumentException) as e:
         eng.forward(np.ones(20), np.ones(8), np.ones(8), 3, 0)
     assert e.value.getErrorCode() == vw.ErrorCode.VAL_TOO_LARGE
+
+
+def test_parallel_multilevel_variant_and_factory():
+    # CORE/modwt/ParallelMultiLevelMODWT.java:84-176 == the sequential cascade (ParallelVsSequentialEquivalenceTest.java
+    # :18-49, 1e-12, N in {256, 500}, PERIODIC + ZERO_PADDING); SYMMETRIC is computed as ZERO_PADDING there (D6)
+    h, g, _ = filters("db4")
+    for n in (256, 500):
+        x = composite_sin(n, 11, 0.2)
+        par = vw.ParallelMultiLevelMODWT()
+        for mode in MODES:
+            r = par.decompose(x, vw.Daubechies.DB4, mode, 3)
+            eff = 0 if mode == BM.PERIODIC else 1
+            w, v = cref.decompose(x, h, g, 3, eff)
+            close(r._w, w, x)
+            close(r._v, v, x)
+        with pytest.raises(vw.InvalidArgumentException):
+            par.decompose(x, vw.Daubechies.DB4, BM.PERIODIC, 0)
+    t = vw.MODWTTransformFactory.createMultiLevel(vw.Daubechies.DB4)
+    assert t.getBoundaryMode() == BM.PERIODIC and isinstance(vw.MODWTTransformFactory.create(vw.Haar.INSTANCE if hasattr(vw.Haar, "INSTANCE") else vw.get_wavelet("haar")), vw.MODWTTransform)

@@ -9,8 +9,9 @@ from .batch import BatchMODWT, BatchSIMDMODWT, MultiLevelResult, SingleLevelResu
 from .denoising import ThresholdMethod, ThresholdType, WaveletDenoiser  # noqa: F401
 from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentException, InvalidSignalException,  # noqa: F401
                      NativeEngineError, NullPointerException, WaveletTransformException)
-from .modwt import (MODWTResult, MODWTTransform, MultiLevelMODWTResult, MultiLevelMODWTTransform,  # noqa: F401
-                    MutableMultiLevelMODWTResult, SymmetricAlignmentStrategy)
+from .modwt import (MODWTResult, MODWTTransform, MODWTTransformFactory, MultiLevelMODWTResult,  # noqa: F401
+                    MultiLevelMODWTTransform, MutableMultiLevelMODWTResult, ParallelMultiLevelMODWT,
+                    SymmetricAlignmentStrategy)
 from .ops import WaveletOperations  # noqa: F401
 from .streaming import BatchStreamingMODWT  # noqa: F401
 from .swt import VectorWaveSwtAdapter  # noqa: F401

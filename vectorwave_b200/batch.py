@@ -115,8 +115,27 @@ class BatchMODWT:
         return (engine or Engine.get()).inverse(d, a, hs, gs, _P, None, ORDER_SPLIT)
 
 
+def _soa_rows(soa, batch, n):
+    """flat SoA [t*batch + b] -> [batch][n] rows, staying on the device for CUDA tensors (zero host round trips)"""
+    if _is_torch(soa):
+        return soa.reshape(n, batch).t().contiguous()
+    return np.ascontiguousarray(np.asarray(soa, dtype=np.float64).reshape(n, batch).T)
+
+
+def _rows_to_soa(rows, out):
+    """[batch][n] rows -> the caller's flat SoA array (numpy or torch, written in place)"""
+    if _is_torch(out):
+        import torch
+        src = rows if _is_torch(rows) else torch.as_tensor(rows, device=out.device)
+        out.reshape(rows.shape[1], rows.shape[0]).copy_(src.t())
+    else:
+        r = rows.cpu().numpy() if _is_torch(rows) else rows
+        out[...] = np.ascontiguousarray(r.T).ravel()
+
+
 class BatchSIMDMODWT:
-    """SoA statics: flat arrays indexed t*batchSize + b (BatchSIMDMODWT.java:282-308)."""
+    """SoA statics: flat arrays indexed t*batchSize + b (BatchSIMDMODWT.java:282-308).  numpy arrays or CUDA
+    tensors; with CUDA tensors the SoA <-> row transposes run on the device and nothing crosses PCIe."""
 
     @staticmethod
     def convertToSoA(signals, soaOutput=None):
@@ -136,11 +155,11 @@ class BatchSIMDMODWT:
     @staticmethod
     def batchMODWTSoA(soaSignals, soaApprox, soaDetail, wavelet, batchSize, signalLength, engine=None):
         """:64-81; outputs written into the caller's SoA arrays."""
-        x = np.ascontiguousarray(np.asarray(soaSignals, dtype=np.float64).reshape(signalLength, batchSize).T)
+        x = _soa_rows(soaSignals, batchSize, signalLength)
         hs, gs = _scaled(wavelet, True)
         w, v = (engine or Engine.get()).forward(x, hs, gs, 1, _P)
-        soaApprox[...] = np.ascontiguousarray(v.T).ravel()
-        soaDetail[...] = np.ascontiguousarray(w[0].T).ravel()
+        _rows_to_soa(v, soaApprox)
+        _rows_to_soa(w[0], soaDetail)
 
     @staticmethod
     def batchMultiLevelMODWTSoA(soaSignals, soaDetailPerLevel, soaApproxOut, wavelet, batchSize, signalLength,
@@ -148,10 +167,10 @@ class BatchSIMDMODWT:
         """:343-381"""
         if len(soaDetailPerLevel) != levels:
             raise IllegalArgumentException("soaDetailPerLevel length must equal levels")
-        x = np.ascontiguousarray(np.asarray(soaSignals, dtype=np.float64).reshape(signalLength, batchSize).T)
+        x = _soa_rows(soaSignals, batchSize, signalLength)
         hs, gs = _scaled(wavelet, False)
         _check_levels(x, hs.size, levels)
         w, v = (engine or Engine.get()).forward(x, hs, gs, levels, _P)
         for j in range(levels):
-            soaDetailPerLevel[j][...] = np.ascontiguousarray(w[j].T).ravel()
-        soaApproxOut[...] = np.ascontiguousarray(v.T).ravel()
+            _rows_to_soa(w[j], soaDetailPerLevel[j])
+        _rows_to_soa(v, soaApproxOut)

@@ -480,3 +480,62 @@ class MultiLevelMODWTTransform:
         for level in range(minLevel, maxLevel + 1):
             mask |= 1 << (level - 1)
         return self._reconstruct(result, mask, levels <= maxLevel)
+
+
+# ---------------------------------------------------------------------------------------------
+# ParallelMultiLevelMODWT / MODWTTransformFactory (thin host classes over the same engine calls)
+# ---------------------------------------------------------------------------------------------
+class ParallelMultiLevelMODWT:
+    """CORE/modwt/ParallelMultiLevelMODWT.java:84-176.  The reference runs the h and g convolutions of a level on an
+    executor; here the level is one kernel launch anyway, so only its observable quirks are mirrored: any
+    non-PERIODIC mode -- SYMMETRIC included -- is computed as ZERO_PADDING (:125-129,156-162), and the
+    level admissibility uses `n < L` instead of `n <= L` (:225)."""
+
+    MAX_DECOMPOSITION_LEVELS = 10
+
+    def __init__(self, parallelism=0, engine=None):
+        self._engine = engine
+
+    def _calculate_max_levels(self, n, l):
+        if n < l:
+            return 0
+        max_level = 1
+        while max_level < self.MAX_DECOMPOSITION_LEVELS:
+            if (l - 1) * (1 << (max_level - 1)) + 1 > n:
+                break
+            max_level += 1
+        return max_level - 1
+
+    def decompose(self, signal, wavelet, mode, levels):
+        if signal is None:
+            raise NullPointerException("signal cannot be null")
+        x = _as_signal(signal)
+        if _length(x) == 0:
+            raise InvalidSignalException("Signal cannot be empty", ErrorCode.VAL_EMPTY)
+        hs, gs = wavelet.lowPassDecomposition() * SCALE, wavelet.highPassDecomposition() * SCALE
+        max_levels = self._calculate_max_levels(_length(x), hs.size)
+        if levels < 1 or levels > max_levels:
+            raise InvalidArgumentException(f"Invalid number of levels: {levels}. Must be between 1 and {max_levels}",
+                                           ErrorCode.CFG_INVALID_DECOMPOSITION_LEVEL)
+        eng = self._engine or Engine.get()
+        eff = BoundaryMode.PERIODIC if mode == BoundaryMode.PERIODIC else BoundaryMode.ZERO_PADDING
+        w, v = eng.forward(x, hs, gs, levels, eff.value, _native.FLAG_CHECK_FINITE)
+        return MultiLevelMODWTResult(w, v, eng)
+
+    def shutdown(self):
+        pass
+
+    def close(self):
+        pass
+
+
+class MODWTTransformFactory:
+    """CORE/modwt/MODWTTransformFactory.java:120-230: sugar over the two constructors (PERIODIC by default)."""
+
+    @staticmethod
+    def create(wavelet, boundaryMode=BoundaryMode.PERIODIC):
+        return MODWTTransform(wavelet, boundaryMode)
+
+    @staticmethod
+    def createMultiLevel(wavelet, boundaryMode=BoundaryMode.PERIODIC):
+        return MultiLevelMODWTTransform(wavelet, boundaryMode)
