@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -241,7 +241,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,7 +252,8 @@ def main():
 
     # ---- roofline of the dominant kernel: the fused analysis launch(es), timed alone with CUDA events -------
     peak, peak_src = measured_peaks()
-    reps = max(10, args.steps)
+    reps = max(10, args.steps, int(80.0 / max(ms_step / 2.0, 1e-3)))   # >= 80 ms per direction: stable event timing, clock samples
+    reps = min(reps, 2000)
     for _ in range(3):
         eng.forward(xs[0], hs, gs, levels, mode, 0, ws[0], vs[0])
     torch.cuda.synchronize()
@@ -275,6 +275,9 @@ def main():
     g1.record()
     torch.cuda.synchronize()
     inv_ms = g0.elapsed_time(g1) / reps
+    # the sampler ran through the timed steps AND the per-direction loops above (the same kernels under load): a 20-step
+    # timed region of this workload lasts ~8 ms, too short for nvidia-smi's sampling period on its own
+    clocks = sampler.stop() if rank == 0 else None
     alg_bytes_dir = 24.0 * levels * b * n          # 24 B/sample/level/direction
     achieved = alg_bytes_dir / fwd_ms * 1e-6        # GB/s over the forward direction's launches
     roofline = {"bound": "hbm", "kernel": "k_fused_analysis", "achieved": achieved, "peak": peak, "unit": "GB/s",
