@@ -13,6 +13,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_fused_(analysis|synthesis)" --launch-skip 6 -c 2 \
     -o $O/prof_${R}_bench -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_full_$R.log 2>&1
 python tools/prof_once.py --warm 0 > /dev/null 2>&1 && \
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_column|k_fused" -c 14 -o $O/prof_${R}_coif5 -f \
+# (ten forward launches + the first four inverse ones; no source import: gpurun_out/ is capped at 64 MiB per call)
+timeout 900 ncu --set full --clock-control none -k regex:"k_column|k_fused" -c 14 -o $O/prof_${R}_coif5 -f \
     python tools/prof_once.py --warm 0 > $O/ncu_full_coif5_$R.log 2>&1
 ls -la $O/*.ncu-rep
