@@ -324,3 +324,24 @@ def test_pipelined_host_path_equals_oracle(eng, mode):
             eng.forward(bad, *(filters("db4")[i] * S for i in (0, 1)), 3, mode, _native.FLAG_CHECK_FINITE)
     finally:
         eng.set_option("pipe_min", 64 << 20)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("taps", [12, 16, 20, 30])
+def test_long_filters_that_are_not_quadrature_mirrors(eng, mode, taps):
+    """Every orthogonal wavelet takes the QMF builds (only h in uniform registers); an arbitrary (h, g) pair -- e.g. a
+    biorthogonal one -- must take the shared-memory-tap builds of the tile AND column kernels and agree with the oracle."""
+    rng = np.random.default_rng(taps + mode)
+    h = rng.standard_normal(taps) / np.sqrt(taps)
+    g = rng.standard_normal(taps) / np.sqrt(taps)
+    n, levels = 40000, 8 if taps <= 20 else 7
+    x = rng.standard_normal((2, n))
+    w, v = eng.forward(x, h * S, g * S, levels, mode)
+    for i in range(2):
+        wo, vo = cref.decompose(x[i], h, g, levels, mode)
+        np.testing.assert_allclose(w[:, i, :], wo, rtol=0, atol=1e-12 * max(1.0, np.max(np.abs(wo))))
+        np.testing.assert_allclose(v[i], vo, rtol=0, atol=1e-12 * max(1.0, np.max(np.abs(vo))))
+    xr = eng.inverse(w, v, h * S, g * S, mode, None, _native.ORDER_PAIR if mode == 1 else _native.ORDER_SPLIT)
+    for i in range(2):
+        ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, 0)
+        np.testing.assert_allclose(xr[i], ref, rtol=0, atol=1e-12 * max(1.0, np.max(np.abs(ref))))
