@@ -326,7 +326,11 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)
         default: return VW_EUNSUPPORTED;                            \
     }
 
-int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &grid, int &rows_per_chunk, int &chunks_out) {
+// per_sm = CTAs of this kernel build resident on one SM (occupancy query).  The grid is sized to a whole number of
+// waves: with 2-3 resident CTAs per SM a naturally sized grid of ~1800 CTAs ran 4.1 or 6.15 waves, i.e. 12-18 % of the
+// run with most SMs idle (and 2.05 waves -> 68 % at the 2^25-sample spans of an 8-GPU job).
+int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per_sm, dim3 &grid, int &rows_per_chunk,
+             int &chunks_out) {
     if (d < 1 || d > (1ll << 30)) return VW_EUNSUPPORTED;
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
@@ -338,11 +342,24 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, dim3 &g
     if (rpc < 4 * kCR) rpc = 4 * kCR;
     rpc = ((rpc + kCR - 1) / kCR) * kCR;
     chunks = (rows + rpc - 1) / rpc;
-    const int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;
+    int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;
+    const int64_t by = batch < 65535 ? batch : 65535;
+    const int64_t resident = (int64_t)std::max(per_sm, 1) * ctx->sm_count;
+    if (by == 1 && blocks > resident) {   // (batches already run thousands of short CTAs: quantisation is negligible)
+        // shrink to a whole number of waves (never grow: longer chunks only amortise the warm-up better)
+        const int64_t waves = (blocks * by) / resident;
+        const int64_t target = std::max<int64_t>(1, waves * resident / by);            // blocks along x
+        int64_t c2 = std::max<int64_t>(1, target * kCThreads / d);                      // chunks that fit the target
+        int64_t r2 = (rows + c2 - 1) / c2;
+        r2 = ((r2 + kCR - 1) / kCR) * kCR;
+        c2 = (rows + r2 - 1) / r2;
+        const int64_t b2 = (c2 * d + kCThreads - 1) / kCThreads;
+        if (b2 <= blocks && r2 < (1ll << 30)) { rpc = r2; chunks = c2; blocks = b2; }
+    }
     if (blocks > 0x7fffffffll) return VW_EUNSUPPORTED;
     rows_per_chunk = (int)rpc;
     chunks_out = (int)chunks;
-    grid = dim3((unsigned)blocks, (unsigned)(batch < 65535 ? batch : 65535));
+    grid = dim3((unsigned)blocks, (unsigned)by);
     return VW_OK;
 }
 
@@ -358,14 +375,18 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
     if (l < 2 || l > VW_FUSED_MAX_L || n_out < 1 || batch < 1) return VW_EUNSUPPORTED;
     ColArgs a;
     dim3 grid;
-    int rc = geometry(ctx, n_out, d, batch, grid, a.rows_per_chunk, a.chunks);
-    if (rc) return rc;
     a.x = x; a.ldx = ldx; a.w_in = nullptr; a.ldw_in = 0; a.v = v; a.ldv = ldv; a.w = w; a.ldw = ldw;
     a.thr = nullptr; a.thr_per_row = 0; a.thr_soft = 0;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.off_h = a.off_g = 0;
     a.mode = mode;
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < l ? f.h[k] : 0.0; a.f.g[k] = k < l ? f.g[k] : 0.0; }
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);
+    int per_sm = 0;
+#define VW_CO(LL, QQ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis<LL, QQ>, kCThreads, 0)
+    VW_DISPATCH_CL(l, qmf, VW_CO)
+#undef VW_CO
+    int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks);
+    if (rc) return rc;
 #define VW_CA(LL, QQ) k_column_analysis<LL, QQ><<<grid, kCThreads, 0, ctx->stream>>>(a)
     VW_DISPATCH_CL(l, qmf, VW_CA)
 #undef VW_CA
@@ -379,8 +400,6 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
     if (l < 2 || l > VW_FUSED_MAX_L || n_out < 1 || batch < 1) return VW_EUNSUPPORTED;
     ColArgs a;
     dim3 grid;
-    int rc = geometry(ctx, n_out, d, batch, grid, a.rows_per_chunk, a.chunks);
-    if (rc) return rc;
     a.x = v; a.ldx = ldv; a.w_in = w; a.ldw_in = ldw; a.v = out; a.ldv = ldo; a.w = nullptr; a.ldw = 0;
     a.thr = thr_dev; a.thr_per_row = thr_per_row; a.thr_soft = thr_soft;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d;
@@ -393,6 +412,12 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
         a.f.g[k] = k < l ? (al.sigma_g > 0 ? f.g[k] : f.g[l - 1 - k]) : 0.0;
     }
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);   // on the arrays as the kernel sees them (sigma = -1 streams are reversed)
+    int per_sm = 0;
+#define VW_CO(LL, QQ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis<LL, QQ>, kCThreads, 0)
+    VW_DISPATCH_CL(l, qmf, VW_CO)
+#undef VW_CO
+    int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks);
+    if (rc) return rc;
 #define VW_CS(LL, QQ) k_column_synthesis<LL, QQ><<<grid, kCThreads, 0, ctx->stream>>>(a)
     VW_DISPATCH_CL(l, qmf, VW_CS)
 #undef VW_CS
