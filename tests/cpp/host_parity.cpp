@@ -1,0 +1,91 @@
+// Parity of the C++ host mirror (include/vw_modwt.hpp over libvwmodwt.so) against the CPU oracle (oracle/modwt_oracle.c,
+// test infrastructure).  Built and run by tests/test_cpp_host.py on a GPU box; exits 0 and prints "ok" on success.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "vw_modwt.hpp"
+
+extern "C" {
+void vwo_forward_single(const double *x, int64_t n, const double *h, const double *g, int64_t l, int mode, double *v, double *w);
+void vwo_inverse_single(const double *v, const double *w, int64_t n, const double *hr, const double *gr, int64_t l, int mode,
+                        int batch_variant, double *out);
+int vwo_decompose(const double *x, int64_t n, const double *h, const double *g, int64_t l, int levels, int mode, int dense,
+                  double *w, double *v);
+void vwo_reconstruct(const double *w, const double *v, int64_t n, const double *hr, const double *gr, int64_t l, int levels, int mode,
+                     int wavelet_id, int dense, uint64_t detail_mask, int use_approx, double *out);
+double vwo_swt_denoise(const double *x, int64_t n, const double *h, const double *g, int64_t l, int levels, int mode, int wavelet_id,
+                       double thr, int soft, int dense, double *out);
+}
+
+using namespace vectorwave;
+
+static int failures = 0;
+static void expect_close(const std::vector<double> &a, const double *b, double tol, const char *what) {
+    double m = 0;
+    for (size_t i = 0; i < a.size(); i++) m = std::fmax(m, std::fabs(a[i] - b[i]));
+    if (!(m <= tol)) { std::printf("FAIL %s: max diff %.3e > %.3e\n", what, m, tol); failures++; }
+}
+
+int main() {
+    std::mt19937_64 rng(42);
+    std::normal_distribution<double> nd;
+    struct Case { Wavelet w; int oracle_id; };
+    const Case cases[] = {{wavelets::haar(), 0}, {wavelets::db4(), 0}, {wavelets::db8(), 2}, {wavelets::sym8(), 4}, {wavelets::coif5(), 0}};
+    const BoundaryMode modes[] = {BoundaryMode::PERIODIC, BoundaryMode::ZERO_PADDING, BoundaryMode::SYMMETRIC};
+    for (const Case &c : cases) {
+        const std::vector<double> h = c.w.lowPassDecomposition(), g = c.w.highPassDecomposition();
+        const int l = (int)h.size();
+        for (int n : {4096, 1001}) {
+            std::vector<double> x(n);
+            double xmax = 0;
+            for (double &v : x) { v = nd(rng); xmax = std::fmax(xmax, std::fabs(v)); }
+            const double tol = 1e-12 * xmax;   // north_star: 1e-12 * max|x| per level
+            for (BoundaryMode m : modes) {
+                const int mode = (int)m;
+                // single level
+                MODWTTransform t(c.w, m);
+                MODWTResult r = t.forward(x);
+                std::vector<double> v(n), w(n), xr(n);
+                vwo_forward_single(x.data(), n, h.data(), g.data(), l, mode, v.data(), w.data());
+                expect_close(r.approximationCoeffs(), v.data(), tol, "forward V");
+                expect_close(r.detailCoeffs(), w.data(), tol, "forward W");
+                vwo_inverse_single(v.data(), w.data(), n, h.data(), g.data(), l, mode, 0, xr.data());
+                expect_close(t.inverse(MODWTResult(v, w)), xr.data(), tol, "inverse");
+                // multi level
+                MultiLevelMODWTTransform mt(c.w, m);
+                const int levels = std::min(5, mt.getMaximumLevels(n));
+                MultiLevelMODWTResult mr = mt.decompose(x, levels);
+                std::vector<double> wo((size_t)levels * n), vo(n);
+                vwo_decompose(x.data(), n, h.data(), g.data(), l, levels, mode, 0, wo.data(), vo.data());
+                for (int j = 1; j <= levels; j++) expect_close(mr.getDetailCoeffsAtLevel(j), wo.data() + (size_t)(j - 1) * n, tol, "decompose W_j");
+                expect_close(mr.getApproximationCoeffs(), vo.data(), tol, "decompose V_J");
+                vwo_reconstruct(wo.data(), vo.data(), n, h.data(), g.data(), l, levels, mode, c.oracle_id, 0, (1ull << levels) - 1, 1, xr.data());
+                expect_close(mt.reconstruct(mr), xr.data(), tol, "reconstruct");
+                vwo_reconstruct(wo.data(), vo.data(), n, h.data(), g.data(), l, levels, mode, c.oracle_id, 0, ((1ull << levels) - 1) & ~1ull, 1, xr.data());
+                expect_close(mt.reconstructFromLevel(mr, 2), xr.data(), tol, "reconstructFromLevel");
+                // SWT denoise, universal soft threshold
+                VectorWaveSwtAdapter swt(c.w, m);
+                vwo_swt_denoise(x.data(), n, h.data(), g.data(), l, levels, mode, c.oracle_id, -1.0, 1, 0, xr.data());
+                expect_close(swt.denoise(x, levels), xr.data(), tol, "swt denoise");
+            }
+        }
+    }
+    // level cap and errors (CTEST/modwt/MultiLevelMODWTTransformTest.java:271-305)
+    MultiLevelMODWTTransform ht(wavelets::haar(), BoundaryMode::PERIODIC);
+    if (ht.getMaximumLevels(10000) != 9) { std::printf("FAIL level cap\n"); failures++; }
+    try { ht.decompose(std::vector<double>(10000, 1.0), 10); std::printf("FAIL no throw\n"); failures++; } catch (const InvalidArgumentException &) {}
+    try { MODWTTransform(wavelets::db4(), BoundaryMode::CONSTANT); std::printf("FAIL CONSTANT accepted\n"); failures++; } catch (const InvalidArgumentException &) {}
+    try { std::vector<double> bad(64, 1.0); bad[3] = NAN; MODWTTransform(wavelets::db4(), BoundaryMode::PERIODIC).forward(bad); std::printf("FAIL NaN accepted\n"); failures++; }
+    catch (const InvalidSignalException &) {}
+    // batch facade round trip (haar: exact table)
+    std::vector<std::vector<double>> sig(4, std::vector<double>(512));
+    for (auto &s : sig) for (double &v : s) v = nd(rng);
+    auto br = BatchMODWT::multiLevelAoS(wavelets::haar(), sig, 4);
+    std::vector<double> back = BatchMODWT::inverseMultiLevelAoS(wavelets::haar(), br);
+    for (int i = 0; i < 4; i++) expect_close(sig[i], back.data() + (size_t)i * 512, 1e-10, "batch round trip");
+    if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
+    std::printf("ok\n");
+    return 0;
+}
