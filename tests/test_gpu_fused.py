@@ -345,3 +345,44 @@ def test_long_filters_that_are_not_quadrature_mirrors(eng, mode, taps):
     for i in range(2):
         ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, 0)
         np.testing.assert_allclose(xr[i], ref, rtol=0, atol=1e-12 * max(1.0, np.max(np.abs(ref))))
+
+
+@pytest.mark.parametrize("name,b,n,levels,rt_tol", [
+    ("sym8", 1024, 65536, 8, 5e-7),      # config #3 at its full size (0.5 GiB in, 4.5 GiB of coefficients)
+    ("coif5", 1, 1 << 28, 10, 1e-10),    # config #4 at its full size (2 GiB in, 22 GiB of coefficients), J = 10
+    ("db8", 256, 1 << 20, 6, 1e-10),     # config #5 at its full size (2 GiB in, 14 GiB of coefficients)
+])
+def test_baseline_full_sizes(eng, name, b, n, levels, rt_tol):
+    """BASELINE.json configs #3 - #5 at their FULL sizes through size-independent properties: PERIODIC round trip,
+    energy conservation, shift equivariance of one signal, and -- for #5 -- the SWT denoise identities of the
+    SYMMETRIC / ZERO_PADDING modes (a zero threshold reproduces reconstruct(decompose(x)) bit for bit of the same
+    kernels; hard thresholding above max|W| leaves only the approximation branch)."""
+    import torch
+    h, g, _ = filters(name)
+    hs, gs = h * S, g * S
+    x = _device_signal(b, n, 4242)
+    scale = float(x.abs().max())
+    w, v = eng.forward(x, hs, gs, levels, 0)
+    xr = eng.inverse(w, v, hs, gs, 0)
+    assert float((xr - x).abs().max()) <= rt_tol * scale
+    e_in = float((x * x).sum())
+    e_out = float((w * w).sum() + (v * v).sum())
+    assert abs(e_in - e_out) / e_in < 1e-6
+    row = x[:1].clone()
+    w1, _ = eng.forward(row, hs, gs, levels, 0)
+    ws, _ = eng.forward(torch.roll(row, 12345, dims=1), hs, gs, levels, 0)
+    assert float((ws - torch.roll(w1, 12345, dims=2)).abs().max()) <= 1e-12 * scale
+    del xr, ws, w1
+    if name == "db8":
+        from vectorwave_b200.modwt import multilevel_alignment
+        for mode, bm in ((1, vw.BoundaryMode.ZERO_PADDING), (2, vw.BoundaryMode.SYMMETRIC)):
+            align, order = multilevel_alignment(vw.Daubechies.DB8, bm, levels)
+            wm, vm = eng.forward(x, hs, gs, levels, mode, 0, w, v)
+            ref = eng.inverse(wm, vm, hs, gs, mode, align, order)
+            den, thr = eng.denoise(x, hs, gs, levels, mode, align, order, 0.0, True)
+            assert float((den - ref).abs().max()) <= 1e-12 * scale             # zero threshold: plain reconstruct
+            big = float(wm.abs().max()) * 2.0
+            den2, _ = eng.denoise(x, hs, gs, levels, mode, align, order, big, False)
+            approx_only = eng.inverse(wm, vm, hs, gs, mode, align, order, detail_mask=0)
+            assert float((den2 - approx_only).abs().max()) <= 1e-12 * scale    # every detail removed
+            del ref, den, den2, approx_only
