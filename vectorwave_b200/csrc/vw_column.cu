@@ -16,10 +16,16 @@
 namespace {
 
 constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value
-template <int L> struct col_rows { static constexpr int value = L >= 24 ? 8 : 9; };       // analysis
+#ifndef VW_COL_RA
+#define VW_COL_RA 10
+#endif
+#ifndef VW_COL_RS
+#define VW_COL_RS 10
+#endif
+template <int L> struct col_rows { static constexpr int value = L >= 24 ? VW_COL_RA : 9; };       // analysis
 // synthesis keeps L-1+R running sums: long filters take R = 10 at two CTAs per SM (254 registers, no spills) -- fewer
 // window shifts per FMA beat the third CTA (measured on coif5)
-template <int L> struct col_rows_syn { static constexpr int value = L >= 24 ? 10 : (L >= 16 ? 8 : 9); };
+template <int L> struct col_rows_syn { static constexpr int value = L >= 24 ? VW_COL_RS : (L >= 16 ? 8 : 9); };
 constexpr int kCThreads = 128;
 
 // Tap delivery.  sm_100 ptxas never folds a constant-bank operand into DFMA: taps go through uniform registers, and
@@ -345,7 +351,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
     int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;
     const int64_t by = batch < 65535 ? batch : 65535;
     const int64_t resident = (int64_t)std::max(per_sm, 1) * ctx->sm_count;
-    if (by == 1 && blocks > resident) {   // (batches already run thousands of short CTAs: quantisation is negligible)
+    if (ctx->opt_wave != 0 && by == 1 && blocks > resident) {   // (batches already run thousands of short CTAs: quantisation is negligible)
         // shrink to a whole number of waves (never grow: longer chunks only amortise the warm-up better)
         const int64_t waves = (blocks * by) / resident;
         const int64_t target = std::max<int64_t>(1, waves * resident / by);            // blocks along x
@@ -365,9 +371,14 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
 
 }  // namespace
 
-int vw_column_min_level(const vw_ctx *ctx, int l) {
+int vw_column_min_level(const vw_ctx *ctx, int l, bool forward) {
     if (ctx->opt_colmin > 0) return (int)ctx->opt_colmin;
-    return l >= 24 ? 3 : 6;
+    // measured on coif5 at 2^28 samples: analysis column 1.26 / 1.18 ms at dilation 4 / 8 vs 1.37 ms tile kernel; for the
+    // synthesis the two are within noise of each other (the planner's small tile at those levels loses what the tile
+    // kernel gains), so both directions switch at level 3
+    (void)forward;
+    if (l >= 24) return 3;
+    return 6;
 }
 
 int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int64_t ldv, double *w, int64_t ldw,

@@ -714,7 +714,7 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
         for (int nf = 1; nf <= cap && done + nf <= levels; nf++) {
             int64_t tile;
             double c = group_cost(ctx, forward, l, done + 1, nf, n, &tile);
-            if (nf == 1 && done + 1 >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
+            if (nf == 1 && done + 1 >= vw_column_min_level(ctx, l, forward) && ctx->opt_poly != 0) {
                 // deep single level (dilation >= 32): the column kernel streams 24 B/sample with no halo recompute
                 bool has = l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12 || l == 16 || l == 18 || l == 20 || l == 30;
                 const double ccol = std::max(2.0 * l / 64.0 / 0.70, 24.0 / 22.5 / 0.80) + 0.1;

@@ -58,6 +58,7 @@ struct vw_ctx {
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
+    int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)
 };
 
@@ -125,8 +126,8 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
 int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f);
 
 // first level (1-based) the column kernels take for filter length l: dilation >= 32 normally; FP64-bound filters
-// (l >= 24) already from dilation 4, where a warp still touches whole 32-byte sectors
-int vw_column_min_level(const vw_ctx *ctx, int l);
+// (l >= 24) already from dilation 4 (analysis) / 16 (synthesis, whose two input streams suffer more from 32-byte row pieces)
+int vw_column_min_level(const vw_ctx *ctx, int l, bool forward = true);
 // ---- deep single levels, dilation >= 32 (vw_column.cu): register sliding window per dilation column ---------
 int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int64_t ldv, double *w, int64_t ldw,
                        int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode);

@@ -252,7 +252,7 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                 const bool fast = !exact && !(flags & VW_FLAG_NO_FUSE);
                 // aligned (sigma, tau) stages have no multi-level fused form: column kernels from dilation 4, and the
                 // single-level tile kernel (stream offsets + reversed taps) below that
-                const int col_min = allow_fused ? vw_column_min_level(ctx, l) : std::min(3, vw_column_min_level(ctx, l));
+                const int col_min = allow_fused ? vw_column_min_level(ctx, l, false) : std::min(3, vw_column_min_level(ctx, l, false));
                 if (fast && level >= col_min && ctx->opt_poly != 0) {
                     rc = vw_column_synthesis(ctx, cur, ld_cur, wj, ldw, out, ld_out, n, 0, n, batch, f, l,
                                              (int64_t)1 << (level - 1), mode, al, thr_dev, thr_per_row, thr_soft);
@@ -473,6 +473,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "threads")) ctx->opt_threads = value;
     else if (!strcmp(name, "poly")) ctx->opt_poly = value;
     else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
+    else if (!strcmp(name, "wave")) ctx->opt_wave = value;
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
     return VW_OK;
@@ -978,7 +979,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
     const bool exact = flags & VW_FLAG_BITEXACT;
     const int64_t n_in = halo + n_local;
     rc = VW_EUNSUPPORTED;
-    const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0;
+    const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l, false) && ctx->opt_poly != 0;
     if (!exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
         VwFusedInv p{vin, n_in, w, n_in, level_stride_w, nlevels >= 64 ? ~0ull : ((1ull << nlevels) - 1), vout, n_local,
                      1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0, 0};
@@ -1000,7 +1001,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                 dst = (double *)p;
             }
             rc = VW_EUNSUPPORTED;
-            if (nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= ((int64_t)1 << (vw_column_min_level(ctx, l) - 1)) && ctx->opt_poly != 0) {
+            if (nlevels == 1 && !exact && !(flags & VW_FLAG_NO_FUSE) && d >= ((int64_t)1 << (vw_column_min_level(ctx, l, false) - 1)) && ctx->opt_poly != 0) {
                 rc = vw_column_synthesis(ctx, cur, 0, w, 0, dst, 0, n_in, 0, n_out, 1, f, l, d, VW_MODE_LINEAR, default_align());
                 if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
             }
