@@ -386,3 +386,47 @@ def test_baseline_full_sizes(eng, name, b, n, levels, rt_tol):
             approx_only = eng.inverse(wm, vm, hs, gs, mode, align, order, detail_mask=0)
             assert float((den2 - approx_only).abs().max()) <= 1e-12 * scale    # every detail removed
             del ref, den, den2, approx_only
+
+
+def test_seeded_random_shapes_against_the_oracle(eng):
+    """A deterministic sweep of 90 random (wavelet, length, levels, mode, batch) shapes -- odd and tiny lengths, lengths
+    just above the level limit, ragged tiles, deep levels -- through forward and inverse, against the oracle."""
+    from vectorwave_b200.modwt import multilevel_alignment
+    rng = np.random.default_rng(20261018)
+    names = ["haar", "db2", "db4", "db6", "db8", "db10", "sym4", "sym8", "coif2", "coif3", "coif5"]
+    bms = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC]
+    done = 0
+    while done < 90:
+        name = names[int(rng.integers(len(names)))]
+        h, g, wid = filters(name)
+        l = len(h)
+        kind = int(rng.integers(4))
+        if kind == 0:
+            n = int(rng.integers(l + 1, 4 * l + 40))                     # tiny: barely admits a level or two
+        elif kind == 1:
+            n = int(rng.integers(500, 20000)) | 1                        # odd: no bulk-copy path
+        elif kind == 2:
+            n = 2 * int(rng.integers(300, 40000))                        # even, ragged against every tile size
+        else:
+            n = 1 << int(rng.integers(9, 17))
+        jmax = cref.max_levels(n, l, 0)
+        if jmax < 1:
+            continue
+        levels = int(rng.integers(1, min(jmax, 11) + 1))
+        if kind == 0 and rng.random() < 0.5:
+            levels = jmax                                                # (L-1)*2^(J-1)+1 just fits
+        mode = int(rng.integers(3))
+        b = int(rng.integers(1, 5))
+        x = rng.standard_normal((b, n)) * float(10.0 ** rng.integers(-3, 4))
+        t = REL * max(float(np.max(np.abs(x))), 1e-300)
+        w, v = eng.forward(x, h * S, g * S, levels, mode)
+        align, order = multilevel_alignment(vw.get_wavelet(name), bms[mode], levels)
+        xr = np.asarray(eng.inverse(w, v, h * S, g * S, mode, align, order))
+        for i in range(b):
+            wo, vo = cref.decompose(x[i], h, g, levels, mode)
+            ctx = f"{name} n={n} J={levels} mode={mode} b={b}"
+            assert float(np.max(np.abs(w[:, i, :] - wo))) <= t, ctx
+            assert float(np.max(np.abs(v[i] - vo))) <= t, ctx
+            ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, wid)
+            assert float(np.max(np.abs(xr[i] - ref))) <= t * 4, ctx
+        done += 1
