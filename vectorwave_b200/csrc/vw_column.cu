@@ -282,8 +282,11 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
     }
 }
 
+#ifndef VW_COL_CS
+#define VW_COL_CS 2
+#endif
 template <int L, bool QMF>
-__global__ void __launch_bounds__(kCThreads, (L >= 24) ? 2 : ((L >= 16) ? 3 : 4)) k_column_synthesis(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kCThreads, (L >= 24) ? VW_COL_CS : ((L >= 16) ? 3 : 4)) k_column_synthesis(const __grid_constant__ ColArgs a) {
     constexpr bool ST = col_smem_taps_syn<L>::value && !QMF;
     __shared__ double2 s_taps[ST ? L : 1];
     if (ST) {
