@@ -50,7 +50,7 @@ for r in rows[2:]:
                      for c in stall_cols), reverse=True)[:4]
     st = ", ".join(f"{n} {v:.2f}" for v, n in stalls)
     print(f"| {r[ix['ID']]} | {name} | {r[ix['Grid Size']]} x {r[ix['Block Size']]} | {us:.1f} | {rd/1e6:.1f} | {wr/1e6:.1f} | "
-          f"{(rd+wr)/us/1e3:.0f} | {val(r,'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+          f"{(rd+wr)/us/1e3:.0f} | {val(r,'dram__bytes_read.sum.pct_of_peak_sustained_elapsed', 0.0) + val(r,'dram__bytes_write.sum.pct_of_peak_sustained_elapsed', 0.0):.1f} | "
           f"{val(r,'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):.1f} | "
           f"{val(r,'sm__issue_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
           f"{val(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {val(r,'launch__registers_per_thread'):.0f} | "
