@@ -15,6 +15,8 @@ CONFIGS = {
     "c2_haar": ("haar", 4096, 4096, 4),
     "c2_db4": ("db4", 4096, 4096, 4),
     "c2s_db4": ("db4", 16, 4096, 4),
+    "c2_db4_j1": ("db4", 4096, 4096, 1),
+    "c2_db4_j2": ("db4", 4096, 4096, 2),
     "c3_sym8": ("sym8", 1024, 65536, 8),
     "c4_coif5": ("coif5", 1, 1 << 28, 10),
     "c4_haar": ("haar", 1, 1 << 28, 10),
