@@ -203,6 +203,14 @@ VW_API int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n,
 VW_API int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out,
                      double *var_out, uint32_t flags);
 
+/* WaveletDenoiser.calculateSUREThreshold (CORE/denoising/WaveletDenoiser.java:441-492) per row: the candidate t = |c_i|
+ * of minimal Stein risk (first minimum in ascending t), every risk accumulated in the reference's coefficient order and
+ * roundings (bit-identical to the JVM's O(n^2) double loop, which is what it costs here too: batch * n^2 <= 2^44), then
+ * capped at sigma * sqrt(2 ln n).  sigma: `batch` doubles on the HOST (noise sigma per row); thr_out: `batch` doubles on
+ * the HOST; risk_out (may be NULL): the minimal risk per row. */
+VW_API int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma,
+                      double *thr_out, double *risk_out, uint32_t flags);
+
 /* sum of squares per row: MultiLevelMODWTResult.getDetailEnergyAtLevel / getApproximationEnergy
  * (CORE/modwt/MultiLevelMODWTResultImpl.java:91-139).  out: `batch` doubles on the HOST. */
 VW_API int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags);

@@ -232,7 +232,7 @@ def _seq_sum(a):
 
 
 def denoiser_threshold(coeffs, sigma, method):
-    """calculateThreshold (:391-436) for UNIVERSAL / MINIMAX / BAYES"""
+    """calculateThreshold (:391-436) for UNIVERSAL / SURE / MINIMAX / BAYES"""
     import math
     n = len(coeffs)
     if method == "UNIVERSAL":
@@ -249,7 +249,35 @@ def denoiser_threshold(coeffs, sigma, method):
         mean = _seq_sum(coeffs) / n
         variance = _seq_sum((np.asarray(coeffs) - mean) ** 2) / n
         return sigma2 / math.sqrt(max(0.0, variance - sigma2) + 1e-10)
+    if method == "SURE":
+        return sure_threshold(coeffs, sigma)[0]
     raise ValueError(method)
+
+
+def sure_threshold(coeffs, sigma):
+    """calculateSUREThreshold + calculateSURERisk (:441-492): every candidate t = sorted |c|[k] scored with a sequential
+    pass over the coefficients in their stored order (vectorised over the candidates, so each risk sees exactly the
+    reference's additions in the reference's order); first strict minimum in ascending k; capped at the universal
+    threshold.  Returns (threshold, minimal risk)."""
+    import math
+    c = np.asarray(coeffs, dtype=np.float64)
+    n = c.size
+    t = np.sort(np.abs(c))                                  # :445-449
+    sigma2 = sigma * sigma
+    risk = np.full(n, float(-n) * sigma2)                   # :480
+    with np.errstate(invalid="ignore", over="ignore"):
+        for cj in c:                                        # :482-489
+            a = abs(cj)
+            d = a - t
+            risk = risk + np.where(a <= t, cj * cj, sigma2 + d * d)
+        risk = risk / n                                     # :491
+    min_risk, best = math.inf, 0.0                          # :452-453
+    ok = risk < math.inf
+    if ok.any():
+        min_risk = float(risk[ok].min())
+        best = float(t[np.flatnonzero(risk == min_risk)[0]])   # `risk < minRisk` keeps the first
+    universal = sigma * math.sqrt(2.0 * math.log(n))        # :465-469
+    return (universal if best > universal else best), min_risk
 
 
 def denoiser_sigma(detail):

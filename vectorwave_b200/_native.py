@@ -82,6 +82,7 @@ SIGNATURES = {
     "vw_energy": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
     "vw_median_abs": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
     "vw_mean_variance": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _u32]),
+    "vw_sure_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _dp, _u32]),
     "vw_modwt_stream_level": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _vp, _i64, _vp, _i64, _u32]),
     "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
     "vw_modwt_inverse_span": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _i32, _vp, _u32]),
@@ -414,6 +415,20 @@ class Engine:
             self._check(self.lib.vw_mean_variance(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                                   m.ctypes.data_as(_dp), v.ctypes.data_as(_dp), fl))
         return (float(m[0]), float(v[0])) if one_d else (m, v)
+
+    def sure_threshold(self, c, sigma, flags=0, with_risk=False):
+        """WaveletDenoiser.calculateSUREThreshold per row (the reference's O(n^2) risk scan, bit for bit, on the device)"""
+        c2, one_d = self._rows(c, "coefficients")
+        sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (c2.shape[0],)))
+        thr, risk = np.empty(c2.shape[0]), np.empty(c2.shape[0])
+        fl = self._bind_stream(c2) | flags
+        with self._call_lock:
+            self._check(self.lib.vw_sure_threshold(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
+                                                   sg.ctypes.data_as(_dp), thr.ctypes.data_as(_dp),
+                                                   risk.ctypes.data_as(_dp), fl))
+        if with_risk:
+            return (float(thr[0]), float(risk[0])) if one_d else (thr, risk)
+        return float(thr[0]) if one_d else thr
 
     def energy(self, c, flags=0):
         c2, one_d = self._rows(c, "coefficients")

@@ -141,5 +141,8 @@ int vw_launch_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, 
                                   double *thr_dev);
 // same selection, raw median(|c|) per row
 int vw_launch_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *med_dev);
+size_t vw_sure_workspace(int64_t batch, int64_t n);
+int vw_launch_sure(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma_dev, void *ws,
+                   double *thr_dev, double *risk_dev);
 int vw_launch_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_dev,
                             double *var_dev);

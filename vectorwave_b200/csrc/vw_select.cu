@@ -213,3 +213,107 @@ static int select_median(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "universal threshold launch");
 }
+
+// ---- SURE threshold (CORE/denoising/WaveletDenoiser.java:441-492) -------------------------------------------------
+// The reference scores every candidate threshold t = |c_i| with a full pass over the coefficients (an O(n^2) double
+// loop) and keeps the first minimum in ascending order of t.  Here one thread owns kSureCand candidates and walks the
+// coefficients in the reference's order with the reference's roundings (separate multiplies and adds, no contraction),
+// so every risk is bit-identical to the JVM's; (|c|, c*c) pairs are staged through shared memory and broadcast.  The
+// sort disappears: "first minimum in ascending t" = the smallest t among the candidates of minimal risk.
+namespace {
+constexpr int kSureThreads = 256, kSureCand = 4, kSureChunk = 2048;
+
+struct SureBest { double risk, t; };
+
+__device__ __forceinline__ SureBest sure_better(SureBest a, SureBest b) {
+    if (a.risk < b.risk) return a;
+    if (b.risk < a.risk) return b;
+    a.t = a.t < b.t ? a.t : b.t;
+    return a;
+}
+
+__global__ void __launch_bounds__(kSureThreads) k_sure_scan(const double *__restrict__ c, int64_t batch, int64_t n, int64_t ld,
+                                                            const double *__restrict__ sigma, SureBest *partial) {
+    __shared__ double2 sm[kSureChunk];
+    __shared__ SureBest red[kSureThreads / 32];
+    for (int64_t row = blockIdx.y; row < batch; row += gridDim.y) {
+        const double *r = c + row * ld;
+        const double sigma2 = __dmul_rn(sigma[row], sigma[row]);             // :479
+        double t[kSureCand], risk[kSureCand];
+        const int64_t i0 = ((int64_t)blockIdx.x * kSureThreads + threadIdx.x) * kSureCand;
+#pragma unroll
+        for (int q = 0; q < kSureCand; q++) {
+            t[q] = i0 + q < n ? fabs(r[i0 + q]) : 0.0;
+            risk[q] = __dmul_rn((double)(-(long long)n), sigma2);            // :480  -n * sigma2
+        }
+        for (int64_t j0 = 0; j0 < n; j0 += kSureChunk) {
+            const int m = (int)(n - j0 < kSureChunk ? n - j0 : kSureChunk);
+            __syncthreads();
+            for (int j = threadIdx.x; j < m; j += kSureThreads) {
+                const double x = r[j0 + j];
+                sm[j] = make_double2(fabs(x), __dmul_rn(x, x));
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int j = 0; j < m; j++) {
+                const double2 p = sm[j];
+#pragma unroll
+                for (int q = 0; q < kSureCand; q++) {
+                    const double d = __dsub_rn(p.x, t[q]);
+                    const double over = __dadd_rn(sigma2, __dmul_rn(d, d));  // :487
+                    risk[q] = __dadd_rn(risk[q], p.x <= t[q] ? p.y : over);  // :484-488 (NaN compares false: else branch)
+                }
+            }
+        }
+        SureBest best{INFINITY, 0.0};                                        // :452-453 minRisk = +inf, bestThreshold = 0
+#pragma unroll
+        for (int q = 0; q < kSureCand; q++) {
+            const double rk = __ddiv_rn(risk[q], (double)n);                 // :491
+            if (i0 + q < n && rk < INFINITY) best = sure_better(best, SureBest{rk, t[q]});   // `risk < minRisk` never takes NaN / +inf
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            SureBest other{__shfl_down_sync(0xffffffffu, best.risk, o), __shfl_down_sync(0xffffffffu, best.t, o)};
+            best = sure_better(best, other);
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kSureThreads / 32; w++) best = sure_better(best, red[w]);
+            partial[row * gridDim.x + blockIdx.x] = best;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sure_finish(const SureBest *partial, int per_row, double *thr_out, double *risk_out) {
+    __shared__ SureBest red[8];
+    SureBest best{INFINITY, 0.0};
+    for (int i = threadIdx.x; i < per_row; i += 256) best = sure_better(best, partial[(int64_t)blockIdx.x * per_row + i]);
+    for (int o = 16; o > 0; o >>= 1) {
+        SureBest other{__shfl_down_sync(0xffffffffu, best.risk, o), __shfl_down_sync(0xffffffffu, best.t, o)};
+        best = sure_better(best, other);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) best = sure_better(best, red[w]);
+        thr_out[blockIdx.x] = best.t;
+        risk_out[blockIdx.x] = best.risk;
+    }
+}
+}  // namespace
+
+size_t vw_sure_workspace(int64_t batch, int64_t n) {
+    const int64_t per_row = (n + kSureThreads * kSureCand - 1) / (kSureThreads * kSureCand);
+    return (size_t)batch * (size_t)per_row * sizeof(SureBest);
+}
+
+int vw_launch_sure(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma_dev, void *ws,
+                   double *thr_dev, double *risk_dev) {
+    if (batch <= 0 || n <= 0) return VW_OK;
+    const int64_t per_row = (n + kSureThreads * kSureCand - 1) / (kSureThreads * kSureCand);
+    const dim3 grid((unsigned)per_row, (unsigned)(batch < 65535 ? batch : 65535));
+    k_sure_scan<<<grid, kSureThreads, 0, ctx->stream>>>(c, batch, n, ld, sigma_dev, (SureBest *)ws);
+    k_sure_finish<<<(unsigned)batch, 256, 0, ctx->stream>>>((const SureBest *)ws, (int)per_row, thr_dev, risk_dev);
+    ctx->launches += 2;
+    return vw_cuda_check(ctx, cudaGetLastError(), "sure launch");
+}

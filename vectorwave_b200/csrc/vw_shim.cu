@@ -830,6 +830,42 @@ int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "mean/variance");
 }
 
+int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma,
+                      double *thr_out, double *risk_out, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
+    if (!sigma || !thr_out) return vw_fail(ctx, VW_ENULL, "sigma and thr_out cannot be null");
+    if ((double)batch * (double)n * (double)n > 17592186044416.0)   // 2^44 candidate x coefficient pairs, a few seconds
+        return vw_fail(ctx, VW_EUNSUPPORTED, "SURE scores n candidates against n coefficients (as the reference does): "
+                                             "batch * n^2 = %.3g exceeds 2^44", (double)batch * (double)n * (double)n);
+    const double *cd = c;
+    int64_t ldd = ld;
+    if (!(flags & VW_FLAG_DEVICE_PTRS)) {
+        void *p;
+        if ((rc = vw_scratch(ctx, 2, (size_t)batch * (size_t)n * 8, &p))) return rc;
+        if ((rc = copy_rows(ctx, p, n, c, ld, n, batch, cudaMemcpyHostToDevice))) return rc;
+        cd = (const double *)p; ldd = n;
+    }
+    void *pt, *ws;
+    if ((rc = vw_scratch(ctx, 5, (size_t)batch * 24 + 64, &pt))) return rc;
+    if ((rc = vw_scratch(ctx, 4, vw_sure_workspace(batch, n), &ws))) return rc;
+    double *sd = (double *)((char *)pt + 64), *td = sd + batch, *rd = td + batch;
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(sd, sigma, (size_t)batch * 8, cudaMemcpyHostToDevice, ctx->stream), "sigma copy")))
+        return rc;
+    if ((rc = vw_launch_sure(ctx, cd, batch, n, ldd, sd, ws, td, rd))) return rc;
+    cudaMemcpyAsync(thr_out, td, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (risk_out) cudaMemcpyAsync(risk_out, rd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "sure"))) return rc;
+    const double root = sqrt(2.0 * log((double)n));
+    for (int64_t b = 0; b < batch; b++) {                           // :465-469 compare with the universal threshold
+        const double universal = sigma[b] * root;
+        if (thr_out[b] > universal) thr_out[b] = universal;
+    }
+    return VW_OK;
+}
+
 int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx->device);

@@ -2,12 +2,14 @@
 
 The reference's denoiser is a caller of the MODWT path: decompose, estimate sigma = median(|W_1|) / 0.6745, pick a
 threshold per level from (W_j, sigma / sqrt(2^j)) with one of the selectors, threshold the details, reconstruct.  Here
-every pass over the coefficients runs on the device (exact median select, mean / variance reductions, thresholding,
-the transforms); only the scalar selector formulas are evaluated on the host, exactly as written in the reference.
+every pass over the coefficients runs on the device (exact median select, mean / variance reductions, the SURE risk
+scan, thresholding, the transforms); only the scalar selector formulas are evaluated on the host, exactly as written in
+the reference.
 
-SURE is the one selector not offered: the reference evaluates the risk of every candidate with an O(n^2) double loop
-(:441-492), and an O(n log n) sort + prefix-sum evaluation changes the summation order enough to flip the arg-min
-between neighbouring candidates -- parity could not be promised, so it raises instead of approximating.
+SURE: the reference evaluates the risk of every candidate with an O(n^2) double loop (:441-492).  A sort + prefix-sum
+evaluation would change the summation order enough to flip the arg-min between neighbouring candidates, so the device
+kernel keeps the double loop -- one thread per candidate, the reference's coefficient order and roundings -- and returns
+the JVM's threshold bit for bit (n = 65536 costs about a millisecond; the engine refuses batch * n^2 > 2^44).
 """
 import enum
 import math
@@ -16,7 +18,7 @@ import numpy as np
 
 from . import _native
 from ._native import ORDER_PAIR
-from .errors import ErrorCode, InvalidArgumentException
+from .errors import ErrorCode, InvalidArgumentException, NativeEngineError
 from .modwt import MODWTTransform, MultiLevelMODWTTransform, _as_signal
 from .wavelets import BoundaryMode, Daubechies
 
@@ -70,10 +72,11 @@ class WaveletDenoiser:
             _, variance = eng.mean_variance(coeffs)
             sigma_x = math.sqrt(max(0.0, variance - sigma2) + BAYES_EPSILON)
             return sigma2 / sigma_x
-        if method == ThresholdMethod.SURE:
-            raise InvalidArgumentException(
-                "SURE threshold selection is not offered by the GPU engine (the reference's O(n^2) risk scan has no "
-                "order-preserving parallel form); use UNIVERSAL, MINIMAX or BAYES", ErrorCode.CFG_UNSUPPORTED_OPERATION)
+        if method == ThresholdMethod.SURE:                          # :441-472
+            try:
+                return eng.sure_threshold(coeffs, sigma)
+            except NativeEngineError as e:                          # n^2 beyond the engine's bound
+                raise InvalidArgumentException(str(e), ErrorCode.CFG_UNSUPPORTED_OPERATION) from e
         if method == ThresholdMethod.FIXED:                         # :414-425
             raise InvalidArgumentException("Fixed threshold method requires explicit threshold value",
                                            ErrorCode.CFG_UNSUPPORTED_OPERATION)
