@@ -16,6 +16,7 @@ ap.add_argument("--log2n", type=int, default=26)
 ap.add_argument("--levels", type=int, default=10)
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--warm", type=int, default=1)
+ap.add_argument("--denoise", type=int, default=0)
 a = ap.parse_args()
 S = 1.0 / math.sqrt(2.0)
 eng = vw.Engine.get()
@@ -29,5 +30,7 @@ xr = torch.empty((a.batch, n), dtype=torch.float64, device="cuda")
 for _ in range(a.warm + 1):
     eng.forward(x, hs, gs, a.levels, a.mode, 0, w, v)
     eng.inverse(w, v, hs, gs, a.mode, None, 1 if a.mode == 1 else 0, out=xr)
+    if a.denoise:
+        eng.denoise(x, hs, gs, a.levels, a.mode, None, 1 if a.mode == 1 else 0, -1.0, True)
 torch.cuda.synchronize()
 print("rt_err", float((xr - x).abs().max()))

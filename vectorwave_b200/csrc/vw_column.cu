@@ -197,6 +197,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
                                                 char *op, int d, int nout, long long pin, uint32_t taps_addr, bool thr_on,
                                                 double lam) {
     constexpr int R = col_rows_syn<L>::value;
+    const bool thr_nonneg = !(lam < 0.0);
     // acc[j] <-> output row  m0 - (L-1) + j ; rows below 0 are never emitted
     double acc[L - 1 + R];
 #pragma unroll
@@ -234,7 +235,7 @@ __device__ __forceinline__ void col_synth_chunk(const ColArgs &a, const double *
     while (in_left > 0) {
         double cv[R], cw[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = thr_on ? vw_threshold_value(nw[r], lam, a.thr_soft) : nw[r]; }
+        for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = thr_on ? (thr_nonneg ? vw_threshold_nonneg(nw[r], lam, a.thr_soft) : vw_threshold_value(nw[r], lam, a.thr_soft)) : nw[r]; }
         if (in_left > R) load_block(R, in_left - R, nv, nw);
         if (col_smem_taps_syn<L>::value && !QMF) {
 #pragma unroll

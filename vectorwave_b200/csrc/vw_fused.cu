@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                    &bars[1 + slot], !have);
     };
     stage_w(top, top & 1);
+    const double lam = a.thr ? a.thr[a.thr_per_row ? b : 0] : 0.0;   // fetched under the first tile's flight
     if (a.use_tma) mbar_wait(&bars[0], 0);
     uint32_t wphase0 = 0, wphase1 = 0;
 
@@ -513,12 +514,24 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         const double *cv = cur + (lev == top ? par_v : 0);
         const int in_ext = extent(lev);
         if (a.thr && have_w) {
-            // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118)
-            const double lam = a.thr[a.thr_per_row ? b : 0];
-            for (int i = tid; i < in_ext; i += (int)blockDim.x) {
-                const double r = vw_threshold_value(wt[i], lam, a.thr_soft);
-                wt[i] = r;
+            // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118): one pass over the
+            // landed tile, 16-byte accesses, four independent pairs in flight per thread (the staging buffer starts
+            // 16-byte aligned; the parity sample in front of an odd start is thresholded too and never read)
+            const bool nonneg = !(lam < 0.0);
+            const int soft = a.thr_soft;
+            auto thr1 = [&](double c) { return nonneg ? vw_threshold_nonneg(c, lam, soft) : vw_threshold_value(c, lam, soft); };
+            double2 *w2 = reinterpret_cast<double2 *>(slot ? wb1 : wb0);
+            const int tot = in_ext + par_w, nt = (int)blockDim.x;
+            const int n2 = (P & 1) ? 0 : tot >> 1;     // odd buffer pitch (no bulk copies): scalar loop below
+            for (int i = tid; i < n2; i += 4 * nt) {
+                double2 q[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (i + k * nt < n2) q[k] = w2[i + k * nt];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i + k * nt < n2) w2[i + k * nt] = make_double2(thr1(q[k].x), thr1(q[k].y));
             }
+            for (int i = 2 * n2 + tid; i < tot; i += nt) { double *wl = reinterpret_cast<double *>(w2) + i; *wl = thr1(*wl); }
             __syncthreads();
         }
         const int ld2 = a.log2d0 + lev;

@@ -71,6 +71,13 @@ __device__ __forceinline__ double vw_threshold_value(double c, double lam, int s
     if (soft) return a > lam ? (c > 0.0 ? m : (c < 0.0 ? -m : c * m)) : 0.0;
     return a <= lam ? 0.0 : c;
 }
+// same value for lam >= 0 (or NaN): |c| > lam then implies c != 0 and not NaN, so signum(c) * m == copysign(m, c) --
+// two FP64-pipe instructions instead of five
+__device__ __forceinline__ double vw_threshold_nonneg(double c, double lam, int soft) {
+    const double a = fabs(c);
+    if (soft) return a > lam ? copysign(a - lam, c) : 0.0;
+    return a <= lam ? 0.0 : c;
+}
 #endif
 
 int vw_fail(vw_ctx *ctx, int status, const char *fmt, ...);
