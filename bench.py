@@ -12,7 +12,8 @@ BASELINE.json configs[1], the extensions batch-facade shape 4096 x 4096 fp64 sig
   roofline  dominant kernel (fused analysis) against the measured HBM copy peak: algorithmic bytes
             (24 B/sample/level) per launch / its CUDA-event duration
   cpu_baseline  the oracle's C restatement of the reference's dense loops (kind "port"; the reference is Java and
-            no JVM exists on the box) on all host cores, same workload (bounded sample)
+            no JVM exists on the box) on all host cores, same workload (bounded sample) = the reference's
+            structured-concurrency baseline; `variants` adds SURVEY 8(d)'s one-thread core scalar and SoA batch lanes
 
 Multi-GPU (torchrun, one rank per GPU): the batch shards by signal with no communication (weak scaling: every
 rank runs the full per-GPU workload); `--workload span` runs one long coif5 signal span-sharded with NCCL halo
@@ -132,6 +133,37 @@ def cpu_port(workload, threads, budget_rows=None, inverse=True):
             "sample": f"{rows} x {n_s} of the {b} x {n} workload, {wname} J={levels}, dense upsampled taps as the "
                       f"reference (Sum_j 2*L_j MACs/sample/direction), {dt:.2f} s, pthread work queue over signals",
             "seconds": dt}
+
+
+def cpu_variants(workload):
+    """SURVEY 8(d)'s other two CPU baselines on one host thread, ~2 s each: (1) the core scalar path (one signal after
+    the other, dense taps, forward + inverse) and (2) the extensions' SoA batch path (lanes = signals, dense taps,
+    forward only as in BatchSIMDMODWT.batchMultiLevelMODWTSoA)."""
+    import numpy as np
+    from oracle import cref
+    from oracle.wavelets import filters
+    wname, b, n, levels, mode = WORKLOADS[workload]
+    h, g, wid = filters(wname)
+    macs_fwd = 2 * sum((len(h) - 1) * (1 << j) + 1 for j in range(levels))
+    n_s = min(n, 1 << 16)
+    out = []
+    rows = max(1, min(b, int(2.0 * 0.4e9 / (2 * macs_fwd * n_s))))
+    x = np.random.default_rng(42).standard_normal((rows, n_s))
+    t0 = time.perf_counter()
+    cref.batch_fwd_inv(x, h, g, levels, mode, wid, dense=True, threads=1, inverse=True)
+    dt = time.perf_counter() - t0
+    out.append({"name": "core_scalar_1_thread", "value": rows * n_s / dt * 1e-9, "unit": UNIT, "cores": 1,
+                "sample": f"{rows} x {n_s}, forward + inverse, {dt:.2f} s"})
+    if mode == 0:
+        lanes = max(1, min(b, int(2.0 * 0.9e9 / (macs_fwd * n_s))))
+        xs = np.ascontiguousarray(np.random.default_rng(43).standard_normal((lanes, n_s)).T).reshape(-1)
+        t0 = time.perf_counter()
+        cref.batch_soa_decompose(xs, lanes, n_s, h, g, levels)
+        dt = time.perf_counter() - t0
+        out.append({"name": "soa_batch_lanes_1_thread_forward_only", "value": lanes * n_s / dt * 1e-9,
+                    "unit": "GSamples/s (forward only)", "cores": 1,
+                    "sample": f"{lanes} lanes x {n_s}, batchMultiLevelMODWTSoA restated (gcc -O2 autovectorised), {dt:.2f} s"})
+    return out
 
 
 def run_reference(args):
@@ -334,6 +366,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         try:
             cpu = cpu_port(args.workload, os.cpu_count() or 1)
+            cpu["variants"] = cpu_variants(args.workload)
         except Exception as ex:  # the checker must never take the bench down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
