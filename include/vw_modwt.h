@@ -203,6 +203,14 @@ VW_API int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n,
 VW_API int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out,
                      double *var_out, uint32_t flags);
 
+/* BatchSIMDMODWT.batchMODWTSoA / batchMultiLevelMODWTSoA (EXT/extensions/modwt/BatchSIMDMODWT.java:64-81,343-424) on
+ * the caller's SoA layout: soa_x[t*batch + b], PERIODIC; soa_w = `levels` pointers (a HOST array, like the reference's
+ * double[][] soaDetailPerLevel) to n*batch doubles each, soa_v = n*batch doubles.  Runs on the flat array as one periodic signal of n*batch samples at dilation 2^(j-1)*batch --
+ * no AoS<->SoA transposes anywhere.  hs/gs: the scaled taps (the reference's Haar special case passes literal +-0.5). */
+VW_API int vw_modwt_forward_soa(vw_ctx *ctx, const double *soa_x, int64_t batch, int64_t n, const double *hs,
+                         const double *gs, int32_t l, int32_t levels, double *const *soa_w, double *soa_v,
+                         uint32_t flags);
+
 /* WaveletDenoiser.calculateSUREThreshold (CORE/denoising/WaveletDenoiser.java:441-492) per row: the candidate t = |c_i|
  * of minimal Stein risk (first minimum in ascending t), every risk accumulated in the reference's coefficient order and
  * roundings (bit-identical to the JVM's O(n^2) double loop, which is what it costs here too: batch * n^2 <= 2^44), then

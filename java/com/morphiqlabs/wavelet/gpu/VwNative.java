@@ -71,6 +71,9 @@ public final class VwNative {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT));
     static final MethodHandle vw_mean_variance = h("vw_mean_variance",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT));
+    /** BatchSIMDMODWT SoA statics in place: (ctx, soa_x, batch, n, hs, gs, l, levels, double*[levels] soa_w, soa_v, flags) */
+    static final MethodHandle vw_modwt_forward_soa = h("vw_modwt_forward_soa",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
     /** WaveletDenoiser.calculateSUREThreshold on the device: (ctx, c, batch, n, ld, sigma[batch], thr_out[batch], risk_out|NULL, flags) */
     static final MethodHandle vw_sure_threshold = h("vw_sure_threshold",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));

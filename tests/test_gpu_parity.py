@@ -367,3 +367,43 @@ def test_parallel_multilevel_variant_and_factory():
             par.decompose(x, vw.Daubechies.DB4, BM.PERIODIC, 0)
     t = vw.MODWTTransformFactory.createMultiLevel(vw.Daubechies.DB4)
     assert t.getBoundaryMode() == BM.PERIODIC and isinstance(vw.MODWTTransformFactory.create(vw.Haar.INSTANCE if hasattr(vw.Haar, "INSTANCE") else vw.get_wavelet("haar")), vw.MODWTTransform)
+
+
+@pytest.mark.parametrize("name,b,n,levels", [("db4", 64, 512, 4), ("haar", 100, 300, 3), ("sym8", 48, 1000, 5),
+                                             ("coif5", 33, 2048, 4), ("db2", 3, 128, 3), ("db4", 8, 256, 3)])
+def test_soa_layout_runs_natively(name, b, n, levels):
+    """BatchSIMDMODWT.batchMultiLevelMODWTSoA on the caller's [t*B+b] layout (no transposes): wide batches take the
+    column kernels at dilation 2^(j-1)*B (any integer B), narrow ones the per-level kernels; host and device buffers."""
+    import torch
+    h, g, _ = filters(name)
+    x = np.random.default_rng(b * 1000 + n).standard_normal((b, n))
+    soa = vw.BatchSIMDMODWT.convertToSoA(x)
+    w_ref, v_ref = nptwin.decompose(x, h, g, levels, 0)                       # [J][B][N], [B][N]
+    w_ref_soa = np.ascontiguousarray(np.transpose(w_ref, (0, 2, 1))).reshape(levels, -1)
+    v_ref_soa = np.ascontiguousarray(v_ref.T).ravel()
+    wv = vw.get_wavelet(name)
+    d = [np.empty(b * n) for _ in range(levels)]
+    a = np.empty(b * n)
+    vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa, d, a, wv, b, n, levels)
+    close(np.stack(d), w_ref_soa, x)
+    close(a, v_ref_soa, x)
+    eng = vw.Engine.get()
+    soa_d = torch.as_tensor(soa, device="cuda")
+    d_d = [torch.full((b * n,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(levels)]
+    a_d = torch.full((b * n,), float("nan"), dtype=torch.float64, device="cuda")
+    l0 = eng.launch_count()
+    vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa_d, d_d, a_d, wv, b, n, levels)
+    assert eng.launch_count() - l0 == levels                                # one kernel per level, nothing else
+    close(np.stack([t.cpu().numpy() for t in d_d]), w_ref_soa, x)
+    close(a_d.cpu().numpy(), v_ref_soa, x)
+    assert torch.equal(soa_d.cpu(), torch.as_tensor(soa))                    # input untouched
+    # bit-exact order on the SoA layout == the reference's SoA loop (same ascending-tap sums per lane)
+    S = 1.0 / math.sqrt(2.0)
+    eng.forward_soa(soa, b, n, np.asarray(h) * S, np.asarray(g) * S, d, a, flags=_native.FLAG_BITEXACT)
+    w_c, v_c = cref.batch_soa_decompose(soa, b, n, h, g, levels)
+    np.testing.assert_array_equal(np.stack(d), w_c)
+    np.testing.assert_array_equal(a, v_c)
+    with pytest.raises(vw.IllegalArgumentException):
+        vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa, d[:-1], a, wv, b, n, levels)
+    with pytest.raises(vw.IllegalArgumentException):
+        vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa, d, np.empty(b * n + 1), wv, b, n, levels)

@@ -82,6 +82,7 @@ SIGNATURES = {
     "vw_energy": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
     "vw_median_abs": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _u32]),
     "vw_mean_variance": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _u32]),
+    "vw_modwt_forward_soa": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _vp, _u32]),
     "vw_sure_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _dp, _u32]),
     "vw_modwt_stream_level": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _vp, _i64, _vp, _i64, _u32]),
     "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
@@ -324,6 +325,27 @@ class Engine:
         if one_d:
             return w[:, 0, :], v[0]
         return w, v
+
+    def forward_soa(self, soa_x, batch, n, hs, gs, soa_w_levels, soa_v, flags=0):
+        """BatchSIMDMODWT SoA layout ([t*batch + b], PERIODIC) in place: flat 1-D arrays, all numpy or all CUDA tensors;
+        soa_w_levels = one flat output per level, soa_v = flat approximation output.  No transposes."""
+        hs, gs = _fp(hs), _fp(gs)
+        levels = len(soa_w_levels)
+        tot = int(batch) * int(n)
+        arrs = [soa_x, soa_v] + list(soa_w_levels)
+        if any(_is_torch(a) for a in arrs) and not all(_is_torch(a) and a.is_cuda for a in arrs):
+            raise IllegalArgumentException("SoA buffers must be all numpy or all CUDA tensors")
+        for a in arrs:
+            ok = (a.is_contiguous() and a.dtype.is_floating_point and a.element_size() == 8) if _is_torch(a) else \
+                (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous)
+            if not ok or (a.numel() if _is_torch(a) else a.size) != tot:
+                raise IllegalArgumentException("SoA buffers must be contiguous float64 arrays of batchSize * signalLength")
+        fl = self._bind_stream(*arrs) | flags
+        ptrs = (C.c_void_p * max(levels, 1))(*[_ptr(a) for a in soa_w_levels])
+        with self._call_lock:
+            self._check(self.lib.vw_modwt_forward_soa(
+                self.ctx, _vp(_ptr(soa_x)), int(batch), int(n), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
+                levels, ptrs, _vp(_ptr(soa_v)), fl))
 
     def inverse(self, w, v, hs, gs, mode, align=None, order=ORDER_SPLIT, detail_mask=None, use_approx=True,
                 flags=0, out=None):

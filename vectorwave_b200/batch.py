@@ -7,7 +7,7 @@ reference's flat `t*batch + b` indexing for drop-in use.  PERIODIC only, like th
 import numpy as np
 
 from ._native import Engine, ORDER_PAIR, ORDER_SPLIT
-from .errors import ErrorCode, IllegalArgumentException, InvalidArgumentException
+from .errors import ErrorCode, IllegalArgumentException, InvalidArgumentException, NullPointerException
 from .modwt import SCALE, _is_torch
 from .wavelets import BoundaryMode, Haar
 
@@ -115,27 +115,34 @@ class BatchMODWT:
         return (engine or Engine.get()).inverse(d, a, hs, gs, _P, None, ORDER_SPLIT)
 
 
-def _soa_rows(soa, batch, n):
-    """flat SoA [t*batch + b] -> [batch][n] rows, staying on the device for CUDA tensors (zero host round trips)"""
-    if _is_torch(soa):
-        return soa.reshape(n, batch).t().contiguous()
-    return np.ascontiguousarray(np.asarray(soa, dtype=np.float64).reshape(n, batch).T)
-
-
-def _rows_to_soa(rows, out):
-    """[batch][n] rows -> the caller's flat SoA array (numpy or torch, written in place)"""
-    if _is_torch(out):
-        import torch
-        src = rows if _is_torch(rows) else torch.as_tensor(rows, device=out.device)
-        out.reshape(rows.shape[1], rows.shape[0]).copy_(src.t())
-    else:
-        r = rows.cpu().numpy() if _is_torch(rows) else rows
-        out[...] = np.ascontiguousarray(r.T).ravel()
+def _soa_flat(a, tot, what, writable=False):
+    """the caller's flat SoA array as the engine wants it: contiguous float64 of batchSize * signalLength, numpy or CUDA
+    tensor; outputs must already be that (they are written in place), inputs are converted if needed"""
+    if a is None:
+        raise NullPointerException(f"{what} cannot be null")
+    if _is_torch(a):
+        if a.numel() != tot:
+            raise IllegalArgumentException(f"{what} length must be batchSize * signalLength")
+        if writable:
+            if not a.is_contiguous():
+                raise IllegalArgumentException(f"{what} must be contiguous")
+            return a.view(-1)
+        return a.contiguous().view(-1)
+    if writable:
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == tot):
+            raise IllegalArgumentException(f"{what} must be a contiguous float64 array of batchSize * signalLength")
+        return a.reshape(-1)
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    if a.size != tot:
+        raise IllegalArgumentException(f"{what} length must be batchSize * signalLength")
+    return a
 
 
 class BatchSIMDMODWT:
-    """SoA statics: flat arrays indexed t*batchSize + b (BatchSIMDMODWT.java:282-308).  numpy arrays or CUDA
-    tensors; with CUDA tensors the SoA <-> row transposes run on the device and nothing crosses PCIe."""
+    """SoA statics: flat arrays indexed t*batchSize + b (BatchSIMDMODWT.java:282-308), numpy arrays or CUDA tensors.
+    The engine runs the cascade on that layout directly (`vw_modwt_forward_soa`: the flat array is one periodic signal of
+    n*B samples at dilation 2^(j-1)*B) -- no AoS <-> SoA transposes, and with CUDA tensors nothing crosses PCIe
+    (SURVEY 8f row 2)."""
 
     @staticmethod
     def convertToSoA(signals, soaOutput=None):
@@ -155,11 +162,11 @@ class BatchSIMDMODWT:
     @staticmethod
     def batchMODWTSoA(soaSignals, soaApprox, soaDetail, wavelet, batchSize, signalLength, engine=None):
         """:64-81; outputs written into the caller's SoA arrays."""
-        x = _soa_rows(soaSignals, batchSize, signalLength)
+        tot = int(batchSize) * int(signalLength)
         hs, gs = _scaled(wavelet, True)
-        w, v = (engine or Engine.get()).forward(x, hs, gs, 1, _P)
-        _rows_to_soa(v, soaApprox)
-        _rows_to_soa(w[0], soaDetail)
+        (engine or Engine.get()).forward_soa(_soa_flat(soaSignals, tot, "soaSignals"), batchSize, signalLength, hs, gs,
+                                             [_soa_flat(soaDetail, tot, "soaDetail", True)],
+                                             _soa_flat(soaApprox, tot, "soaApprox", True))
 
     @staticmethod
     def batchMultiLevelMODWTSoA(soaSignals, soaDetailPerLevel, soaApproxOut, wavelet, batchSize, signalLength,
@@ -167,10 +174,11 @@ class BatchSIMDMODWT:
         """:343-381"""
         if len(soaDetailPerLevel) != levels:
             raise IllegalArgumentException("soaDetailPerLevel length must equal levels")
-        x = _soa_rows(soaSignals, batchSize, signalLength)
+        tot = int(batchSize) * int(signalLength)
         hs, gs = _scaled(wavelet, False)
-        _check_levels(x, hs.size, levels)
-        w, v = (engine or Engine.get()).forward(x, hs, gs, levels, _P)
-        for j in range(levels):
-            _rows_to_soa(w[j], soaDetailPerLevel[j])
-        _rows_to_soa(v, soaApproxOut)
+        # the reference has no L_j <= N validation here and its index goes negative (SURVEY.md D10); reject like core
+        if (hs.size - 1) * (1 << (levels - 1)) + 1 > signalLength:
+            raise InvalidArgumentException("Upsampled analysis filter length exceeds signal length", ErrorCode.VAL_TOO_LARGE)
+        (engine or Engine.get()).forward_soa(_soa_flat(soaSignals, tot, "soaSignals"), batchSize, signalLength, hs, gs,
+                                             [_soa_flat(d, tot, "soaDetailPerLevel", True) for d in soaDetailPerLevel],
+                                             _soa_flat(soaApproxOut, tot, "soaApproxOut", True))

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(kCThreads, (L >= 16) ? 3 : 4) k_column_analysi
     // flattened (chunk, column) index, column fastest: 32 | d keeps every warp inside one chunk => coalesced rows
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
     const int d = (int)a.d;                   // host guarantees d <= 2^30
-    const int col = (int)(gid & (a.d - 1));   // phase phi in [0, d)
     const long long chunk = gid / a.d;
+    const int col = (int)(gid - chunk * a.d);  // phase phi in [0, d); d is any integer (SoA batches: 2^(j-1) * batch)
     if (chunk >= a.chunks) return;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         // rows of this column inside the output range: positions t0 + col + q*d < t0 + n_out
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? VW_COL_CS : ((L >= 16) 
     const uint32_t taps_addr = (uint32_t)__cvta_generic_to_shared(s_taps);
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
     const int d = (int)a.d;
-    const int col = (int)(gid & (a.d - 1));
     const long long chunk = gid / a.d;
+    const int col = (int)(gid - chunk * a.d);   // any integer dilation (SoA batches run at 2^(j-1) * batch)
     if (chunk >= a.chunks) return;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const double *v = a.x ? a.x + b * a.ldx : nullptr;

@@ -627,6 +627,68 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
     return finish(ctx, flags, true);
 }
 
+// SoA batches are one flat periodic signal of n*batch samples whose level-j dilation is 2^(j-1) * batch:
+// x[t*B+b] and x[((t-k d) mod n)*B+b] are d*B apart, and the wrap of the flat index mod n*B is the wrap of t mod n.
+// The column kernels take any integer dilation, so the cascade runs in place on the caller's layout -- no transposes.
+int vw_modwt_forward_soa(vw_ctx *ctx, const double *soa_x, int64_t batch, int64_t n, const double *hs, const double *gs,
+                         int32_t l, int32_t levels, double *const *soa_w, double *soa_v, uint32_t flags) {
+    if (!ctx) return VW_ENULL;
+    DeviceGuard g(ctx->device);
+    int rc;
+    if ((rc = check_signal_args(ctx, soa_x, batch, n, n))) return rc;
+    if (!soa_w || !soa_v) return vw_fail(ctx, VW_ENULL, "output buffers cannot be null");
+    VwFilt f;
+    if ((rc = load_filters(ctx, hs, gs, l, f))) return rc;
+    if ((rc = check_levels(ctx, n, l, levels))) return rc;
+    const int64_t tot = batch * n;
+    for (int j = 0; j < levels; j++)
+        if (!soa_w[j]) return vw_fail(ctx, VW_ENULL, "detail buffer of level %d cannot be null", j + 1);
+    const bool dev = flags & VW_FLAG_DEVICE_PTRS;
+    const bool exact = flags & VW_FLAG_BITEXACT;
+    const double *xd = soa_x;
+    double *wd = nullptr, *vd = soa_v;
+    if (!dev) {
+        void *px, *pw;
+        if ((rc = vw_scratch(ctx, 2, (size_t)tot * 8, &px))) return rc;
+        if ((rc = vw_scratch(ctx, 3, (size_t)tot * 8 * (size_t)(levels + 1), &pw))) return rc;
+        if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(px, soa_x, (size_t)tot * 8, cudaMemcpyHostToDevice, ctx->stream), "h2d"))) return rc;
+        xd = (const double *)px; wd = (double *)pw; vd = wd + (size_t)tot * (size_t)levels;
+    }
+    if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, 1, tot, tot, "signal"))) return rc;
+    const double *cur = xd;
+    double *buf[2] = {nullptr, nullptr};
+    int pp = 0;
+    for (int level = 1; level <= levels; level++) {
+        double *vout = vd;
+        if (level != levels) {
+            if (!buf[pp]) {
+                void *p;
+                if ((rc = vw_scratch(ctx, pp, (size_t)tot * 8, &p))) return rc;
+                buf[pp] = (double *)p;
+            }
+            vout = buf[pp];
+        }
+        const int64_t d = ((int64_t)1 << (level - 1)) * batch;
+        double *wj = dev ? soa_w[level - 1] : wd + (size_t)(level - 1) * (size_t)tot;
+        rc = VW_EUNSUPPORTED;
+        if (!exact && !(flags & VW_FLAG_NO_FUSE) && d >= 32 && ctx->opt_poly != 0) {
+            rc = vw_column_analysis(ctx, cur, 0, vout, 0, wj, 0, tot, 0, tot, 1, f, l, d, VW_PERIODIC);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+        }
+        if (rc == VW_EUNSUPPORTED)   // narrow batches at the first levels, exotic filter lengths, bit-exact order
+            rc = vw_launch_analysis_level(ctx, cur, 0, vout, 0, wj, 0, tot, 0, tot, 1, f, l, d, VW_PERIODIC, exact);
+        if (rc) return rc;
+        cur = vout; pp ^= 1;
+    }
+    if (!dev) {
+        for (int j = 0; j < levels; j++)
+            if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(soa_w[j], wd + (size_t)j * (size_t)tot, (size_t)tot * 8,
+                                                         cudaMemcpyDeviceToHost, ctx->stream), "d2h"))) return rc;
+        if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(soa_v, vd, (size_t)tot * 8, cudaMemcpyDeviceToHost, ctx->stream), "d2h"))) return rc;
+    }
+    return finish(ctx, flags, !dev);
+}
+
 int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_stride_w, const double *vj, int64_t ldv,
                      int64_t batch, int64_t n, const double *hs, const double *gs, int32_t l, int32_t levels,
                      int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask, int32_t use_approx,
