@@ -24,7 +24,10 @@
  *    staged through ctx-owned device memory (pinned host memory from vw_alloc_pinned makes
  *    the copies asynchronous DMA).  There is no CPU compute path: without a CUDA device
  *    vw_init fails with VW_ECUDA and nothing else can be called.
- *  - A ctx is bound to one device and one stream; use one ctx per host thread.
+ *  - A ctx is bound to one device and one stream.  Every call holds the ctx's mutex, so a ctx may be shared between host
+ *    threads (the reference's transform objects are): concurrent calls on one ctx serialise; use one ctx per thread to
+ *    overlap them.  vw_set_stream + the call that follows are two calls -- callers that rebind streams from several
+ *    threads keep their own lock around the pair (the Python mirror does).
  */
 #ifndef VW_MODWT_H
 #define VW_MODWT_H

@@ -406,4 +406,43 @@ struct BatchMODWT {
     }
 };
 
+// ---- BatchSIMDMODWT SoA statics (EXT/extensions/modwt/BatchSIMDMODWT.java:64-81,282-308,343-424) -----------------------
+// flat arrays indexed t*batchSize + b; the engine runs on that layout directly (vw_modwt_forward_soa), no transposes
+struct BatchSIMDMODWT {
+    static void convertToSoA(const std::vector<std::vector<double>> &signals, std::vector<double> &soaOutput) {   // :282-297
+        const size_t b = signals.size(), n = b ? signals[0].size() : 0;
+        soaOutput.resize(b * n);
+        for (size_t t = 0; t < n; t++) for (size_t i = 0; i < b; i++) soaOutput[t * b + i] = signals[i][t];
+    }
+    static void convertFromSoA(const std::vector<double> &soaData, std::vector<std::vector<double>> &output) {   // :299-314
+        const size_t b = output.size(), n = b ? output[0].size() : 0;
+        for (size_t t = 0; t < n; t++) for (size_t i = 0; i < b; i++) output[i][t] = soaData[t * b + i];
+    }
+    static void batchMultiLevelMODWTSoA(const std::vector<double> &soaSignals, std::vector<std::vector<double>> &soaDetailPerLevel,
+                                        std::vector<double> &soaApproxOut, const Wavelet &w, int batchSize, int signalLength, int levels) {
+        if ((int)soaDetailPerLevel.size() != levels) throw IllegalArgumentException("soaDetailPerLevel length must equal levels");
+        const size_t tot = (size_t)batchSize * (size_t)signalLength;
+        if (soaSignals.size() != tot) throw IllegalArgumentException("soaSignals length must be batchSize * signalLength");
+        const std::vector<double> hs = detail::scaled(w.lowPassDecomposition()), gs = detail::scaled(w.highPassDecomposition());
+        std::vector<double *> ptrs;
+        for (auto &d : soaDetailPerLevel) { d.resize(tot); ptrs.push_back(d.data()); }
+        soaApproxOut.resize(tot);
+        Engine &e = Engine::get();
+        e.check(vw_modwt_forward_soa(e.ctx(), soaSignals.data(), batchSize, signalLength, hs.data(), gs.data(), (int)hs.size(), levels,
+                                     ptrs.data(), soaApproxOut.data(), 0));
+    }
+    static void batchMODWTSoA(const std::vector<double> &soaSignals, std::vector<double> &soaApprox, std::vector<double> &soaDetail,
+                              const Wavelet &w, int batchSize, int signalLength) {   // :64-81
+        const size_t tot = (size_t)batchSize * (size_t)signalLength;
+        if (soaSignals.size() != tot) throw IllegalArgumentException("soaSignals length must be batchSize * signalLength");
+        std::vector<double> hs = detail::scaled(w.lowPassDecomposition()), gs = detail::scaled(w.highPassDecomposition());
+        if (w.id() == Wavelet::Id::HAAR) { hs = {0.5, 0.5}; gs = {0.5, -0.5}; }   // literal taps of haarBatchMODWTSoA (:90-93)
+        soaApprox.resize(tot); soaDetail.resize(tot);
+        double *wp = soaDetail.data();
+        Engine &e = Engine::get();
+        e.check(vw_modwt_forward_soa(e.ctx(), soaSignals.data(), batchSize, signalLength, hs.data(), gs.data(), (int)hs.size(), 1, &wp,
+                                     soaApprox.data(), 0));
+    }
+};
+
 }  // namespace vectorwave

@@ -15,6 +15,9 @@ int vwo_decompose(const double *x, int64_t n, const double *h, const double *g, 
                   double *w, double *v);
 void vwo_reconstruct(const double *w, const double *v, int64_t n, const double *hr, const double *gr, int64_t l, int levels, int mode,
                      int wavelet_id, int dense, uint64_t detail_mask, int use_approx, double *out);
+void vwo_batch_soa_decompose(const double *soa_x, int64_t b, int64_t n, const double *h, const double *g, int64_t l, int levels,
+                             double *soa_w, double *soa_v);
+void vwo_batch_soa_haar_single(const double *soa_x, int64_t b, int64_t n, double *soa_v, double *soa_w);
 double vwo_swt_denoise(const double *x, int64_t n, const double *h, const double *g, int64_t l, int levels, int mode, int wavelet_id,
                        double thr, int soft, int dense, double *out);
 }
@@ -85,6 +88,26 @@ int main() {
     auto br = BatchMODWT::multiLevelAoS(wavelets::haar(), sig, 4);
     std::vector<double> back = BatchMODWT::inverseMultiLevelAoS(wavelets::haar(), br);
     for (int i = 0; i < 4; i++) expect_close(sig[i], back.data() + (size_t)i * 512, 1e-10, "batch round trip");
+    // SoA statics on the caller's layout vs the oracle's restatement of the reference SoA loop (48 lanes: column kernels)
+    {
+        const int b = 48, n = 640, levels = 4;
+        std::vector<std::vector<double>> sg(b, std::vector<double>(n));
+        for (auto &s : sg) for (double &v : s) v = nd(rng);
+        std::vector<double> soa, av, wo((size_t)levels * b * n), vo((size_t)b * n);
+        std::vector<std::vector<double>> dl(levels);
+        BatchSIMDMODWT::convertToSoA(sg, soa);
+        BatchSIMDMODWT::batchMultiLevelMODWTSoA(soa, dl, av, wavelets::db4(), b, n, levels);
+        const std::vector<double> h = wavelets::db4().lowPassDecomposition(), g = wavelets::db4().highPassDecomposition();
+        vwo_batch_soa_decompose(soa.data(), b, n, h.data(), g.data(), (int64_t)h.size(), levels, wo.data(), vo.data());
+        for (int j = 0; j < levels; j++) expect_close(dl[j], wo.data() + (size_t)j * b * n, 1e-12 * 6.0, "SoA W_j");
+        expect_close(av, vo.data(), 1e-12 * 6.0, "SoA V_J");
+        std::vector<double> a1, d1;
+        BatchSIMDMODWT::batchMODWTSoA(soa, a1, d1, wavelets::haar(), b, n);
+        std::vector<double> v1((size_t)b * n), w1((size_t)b * n);
+        vwo_batch_soa_haar_single(soa.data(), b, n, v1.data(), w1.data());
+        expect_close(a1, v1.data(), 1e-12 * 6.0, "SoA haar V");
+        expect_close(d1, w1.data(), 1e-12 * 6.0, "SoA haar W");
+    }
     if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
     std::printf("ok\n");
     return 0;

@@ -407,3 +407,42 @@ def test_soa_layout_runs_natively(name, b, n, levels):
         vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa, d[:-1], a, wv, b, n, levels)
     with pytest.raises(vw.IllegalArgumentException):
         vw.BatchSIMDMODWT.batchMultiLevelMODWTSoA(soa, d, np.empty(b * n + 1), wv, b, n, levels)
+
+
+def test_one_context_shared_by_host_threads():
+    """The reference's transform objects are shared between threads (ConcurrentExecutionIntegrationTest): calls on one
+    ctx from several host threads serialise on the ctx mutex.  Raw C-ABI calls here -- the Python mirror's own call lock
+    is bypassed on purpose, and ctypes drops the GIL for the duration of each call."""
+    import ctypes as C
+    import threading
+    eng = vw.Engine.get()
+    S = 1.0 / math.sqrt(2.0)
+    dp = C.POINTER(C.c_double)
+    eng.lib.vw_reset_stream(eng.ctx)
+    jobs = []
+    for i, (name, b, n, levels) in enumerate([("db4", 5, 1024, 4), ("haar", 3, 4096, 5), ("sym8", 7, 2048, 3), ("coif5", 2, 8192, 4)]):
+        h, g, _ = filters(name)
+        x = np.random.default_rng(100 + i).standard_normal((b, n))
+        w_ref, v_ref = nptwin.decompose(x, h, g, levels, 0)
+        jobs.append((x, np.asarray(h) * S, np.asarray(g) * S, levels, w_ref, v_ref))
+    errors = []
+
+    def worker(job):
+        x, hs, gs, levels, w_ref, v_ref = job
+        b, n = x.shape
+        for _ in range(25):
+            w = np.full((levels, b, n), np.nan)
+            v = np.full((b, n), np.nan)
+            rc = eng.lib.vw_modwt_forward(eng.ctx, x.ctypes.data_as(C.c_void_p), b, n, n, hs.ctypes.data_as(dp),
+                                          gs.ctypes.data_as(dp), hs.size, levels, 0, w.ctypes.data_as(C.c_void_p), n, b * n,
+                                          v.ctypes.data_as(C.c_void_p), n, 0)
+            if rc != 0 or not (np.max(np.abs(w - w_ref)) <= tol(x) and np.max(np.abs(v - v_ref)) <= tol(x)):
+                errors.append((rc, x.shape))
+                return
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

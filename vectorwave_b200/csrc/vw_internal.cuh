@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,7 @@ struct vw_ctx {
     int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
+    std::recursive_mutex mu;   // every public entry point holds it: calls on one ctx from several host threads serialise
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)

@@ -52,9 +52,15 @@ int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out) {
 
 namespace {
 
+// Held for the duration of a public call: the ctx's mutex (scratch buffers, stream binding, error string and launch
+// counter are per ctx, so concurrent callers of one ctx serialise -- the reference's transforms are shared across
+// threads) and the ctx's device as the current one.
 struct DeviceGuard {
+    std::unique_lock<std::recursive_mutex> lk;
     int prev = -1;
-    explicit DeviceGuard(int dev) {
+    explicit DeviceGuard(int dev) { enter(dev); }
+    explicit DeviceGuard(vw_ctx *ctx) : lk(ctx->mu) { enter(ctx->device); }
+    void enter(int dev) {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;
@@ -434,7 +440,7 @@ int vw_init(int device, vw_ctx **out) {
 
 int vw_destroy(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2 * vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
@@ -448,19 +454,21 @@ const char *vw_last_error(const vw_ctx *ctx) { return ctx ? ctx->err.c_str() : "
 
 int vw_set_stream(vw_ctx *ctx, void *s) {
     if (!ctx) return VW_ENULL;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ctx->stream = (cudaStream_t)s;
     return VW_OK;
 }
 
 int vw_reset_stream(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ctx->stream = ctx->own_stream;
     return VW_OK;
 }
 
 int vw_synchronize(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
 }
 
@@ -525,24 +533,24 @@ void vw_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 int vw_device_alloc(vw_ctx *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     return vw_cuda_check(ctx, cudaMalloc(out, bytes ? bytes : 16), "vw_device_alloc");
 }
 int vw_device_free(vw_ctx *ctx, void *p) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     return vw_cuda_check(ctx, cudaFree(p), "vw_device_free");
 }
 int vw_copy_h2d(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx || !dst || !src) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "h2d");
     return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "h2d sync");
 }
 int vw_copy_d2h(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx || !dst || !src) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "d2h");
     return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "d2h sync");
 }
@@ -567,7 +575,7 @@ int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels) {
 int vw_conv_modwt(vw_ctx *ctx, const double *x, int64_t n, const double *filter, int64_t lf, int32_t mode, double *out,
                   uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     if (!x || !filter || !out) return vw_fail(ctx, VW_ENULL, "signal, filter and output cannot be null");
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
@@ -594,7 +602,7 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
                      const double *gs, int32_t l, int32_t levels, int32_t mode, double *w, int64_t ldw,
                      int64_t level_stride_w, double *vj, int64_t ldv, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
@@ -633,7 +641,7 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
 int vw_modwt_forward_soa(vw_ctx *ctx, const double *soa_x, int64_t batch, int64_t n, const double *hs, const double *gs,
                          int32_t l, int32_t levels, double *const *soa_w, double *soa_v, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, soa_x, batch, n, n))) return rc;
     if (!soa_w || !soa_v) return vw_fail(ctx, VW_ENULL, "output buffers cannot be null");
@@ -694,7 +702,7 @@ int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_st
                      int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask, int32_t use_approx,
                      double *xout, int64_t ldx, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if (!w || !vj) return vw_fail(ctx, VW_ENULL, "coefficient buffers cannot be null");
@@ -745,7 +753,7 @@ int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_st
 int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t ld, const double *thresholds,
                  int32_t per_row, int32_t soft, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, coeffs, batch, n, ld))) return rc;
     if (!thresholds) return vw_fail(ctx, VW_ENULL, "thresholds cannot be null");
@@ -771,7 +779,7 @@ int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t 
 int vw_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld, double *thresholds_out,
                            uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, w1, batch, n, ld))) return rc;
     if (!thresholds_out) return vw_fail(ctx, VW_ENULL, "thresholds_out cannot be null");
@@ -797,7 +805,7 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
                    const double *gs, int32_t l, int32_t levels, int32_t mode, const vw_align *align, int32_t order,
                    double threshold, int32_t soft, double *out, int64_t ldo, double *thresholds_out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
@@ -848,7 +856,7 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
 
 int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -871,7 +879,7 @@ int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_
 int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out, double *var_out,
                      uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!mean_out || !var_out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -895,7 +903,7 @@ int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int
 int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma,
                       double *thr_out, double *risk_out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!sigma || !thr_out) return vw_fail(ctx, VW_ENULL, "sigma and thr_out cannot be null");
@@ -930,7 +938,7 @@ int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, in
 
 int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -955,7 +963,7 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
                           const double *gs, int32_t l, int32_t first_level, int32_t nlevels, double *w,
                           int64_t level_stride_w, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
@@ -1025,7 +1033,7 @@ int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t
                           const double *hs, const double *gs, int32_t l, int32_t level, double *w, int64_t ldw,
                           double *v, int64_t ldv, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "streaming calls take device pointers only");
     if (!vin || !w || !v) return vw_fail(ctx, VW_ENULL, "stream buffers cannot be null");
@@ -1063,7 +1071,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                           int64_t n_local, const double *hs, const double *gs, int32_t l, int32_t first_level,
                           int32_t nlevels, int32_t order, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
