@@ -307,3 +307,37 @@ def denoiser_multilevel(x, h, g, levels, mode, wavelet_id, method, soft):
         thrs.append(thr)
         wd[j] = threshold(w[j], thr, soft)
     return reconstruct(wd, v, h, g, mode, wavelet_id), thrs
+
+
+class CoreStreamingOracle:
+    """MODWTStreamingTransformImpl (:139-256) / MultiLevelMODWTStreamingTransform (:117-218) restated sample by sample:
+    the ring, the `samplesInBuffer >= bufferSize` trigger, the last-bufferSize-samples window, the L-1 overlap kept after
+    a single-level window, the zero-padded flush.  `windows` collects every window handed to the transform."""
+
+    def __init__(self, buffer_size, filter_length, multilevel):
+        self.bs, self.multilevel = buffer_size, multilevel
+        self.overlap = 0 if multilevel else filter_length - 1
+        self.ring = np.zeros(buffer_size + self.overlap)
+        self.write = 0
+        self.count = 0
+        self.windows = []
+
+    def process(self, data):
+        for sample in data:
+            self.ring[self.write] = sample
+            self.write = (self.write + 1) % self.ring.size
+            self.count += 1
+            if self.count >= self.bs:
+                read = (self.write - self.bs + self.ring.size) % self.ring.size
+                self.windows.append(np.array([self.ring[(read + i) % self.ring.size] for i in range(self.bs)]))
+                self.count -= self.bs - self.overlap
+
+    def flush(self):
+        if self.count > 0:
+            final = np.zeros(self.bs)
+            read = (self.write - self.count + self.ring.size) % self.ring.size
+            for i in range(self.count):
+                final[i] = self.ring[(read + i) % self.ring.size]
+            self.windows.append(final)
+            self.count = 0
+            self.write = 0

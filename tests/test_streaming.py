@@ -107,3 +107,88 @@ def test_streaming_single_level_periodic_state_and_errors():
         vw.BatchStreamingMODWT.Builder().build()
     with pytest.raises(vw.IllegalArgumentException):
         st.processSingleLevel([])
+
+
+# ---- core MODWTStreamingTransform (CORE/modwt/streaming/) ------------------------------------------------------------
+def test_core_streaming_oracle_windows():
+    o = nptwin.CoreStreamingOracle(16, 4, False)          # hop 13
+    o.process(np.arange(50.0))
+    assert [int(w[0]) for w in o.windows] == [0, 13, 26] and o.count == 50 - 39
+    o.flush()
+    assert o.windows[-1][:11].tolist() == list(np.arange(39.0, 50.0)) and not o.windows[-1][11:].any()
+    m = nptwin.CoreStreamingOracle(16, 4, True)
+    m.process(np.arange(40.0))
+    assert [int(w[0]) for w in m.windows] == [0, 16] and m.count == 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_core_streaming_transform_matches_the_reference_windows(mode):
+    import vectorwave_b200 as vw
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    rng = np.random.default_rng(mode)
+    for name, bs in (("db4", 64), ("haar", 32), ("sym8", 256)):
+        h, g, _ = filters(name)
+        data = rng.standard_normal(5 * bs + 17)
+        tol = 1e-12 * float(np.max(np.abs(data)))
+        chunks = [data[:3], data[3:bs + 5], data[bs + 5:bs + 6], data[bs + 6:]]
+        # single level: sliding windows
+        got = []
+        t = vw.MODWTStreamingTransform.create(vw.get_wavelet(name), bm, bs)
+        t.subscribe(got.append)
+        o = nptwin.CoreStreamingOracle(bs, len(h), False)
+        for c in chunks:
+            t.process(c)
+            o.process(c)
+            assert t.getBufferLevel() == o.count
+        t.processSample(0.25)
+        o.process([0.25])
+        assert t.getStatistics().getSamplesProcessed() == data.size + 1
+        assert t.getStatistics().getBlocksProcessed() == len(o.windows)
+        t.close()
+        o.flush()
+        assert t.isClosed() and len(got) == len(o.windows)
+        for r, win in zip(got, o.windows):
+            v, w = nptwin.forward_single(win, h, g, mode)
+            assert np.max(np.abs(r.approximationCoeffs() - v)) <= tol and np.max(np.abs(r.detailCoeffs() - w)) <= tol
+        with pytest.raises(vw.InvalidStateException):
+            t.process(data)
+        # multi level: back-to-back windows, one result per level, approximation on the last only
+        levels = 2
+        got = []
+
+        class Sub:
+            done = False
+
+            def onNext(self, r):
+                got.append(r)
+
+            def onComplete(self):
+                Sub.done = True
+
+        tm = vw.MODWTStreamingTransform.createMultiLevel(vw.get_wavelet(name), bm, bs, levels)
+        tm.subscribe(Sub())
+        om = nptwin.CoreStreamingOracle(bs, len(h), True)
+        for c in chunks:
+            tm.process(c)
+            om.process(c)
+        tm.flush()
+        om.flush()
+        assert tm.getBufferLevel() == 0 and len(got) == levels * len(om.windows)
+        for k, win in enumerate(om.windows):
+            w, v = nptwin.decompose(win, h, g, levels, mode)
+            for level in range(1, levels + 1):
+                r = got[k * levels + level - 1]
+                assert np.max(np.abs(r.detailCoeffs() - w[level - 1])) <= tol
+                if level == levels:
+                    assert np.max(np.abs(r.approximationCoeffs() - v)) <= tol
+                else:
+                    assert r.approximationCoeffs().size == 0
+        tm.close()
+        assert Sub.done
+    with pytest.raises(vw.InvalidArgumentException):
+        vw.MODWTStreamingTransform.create(vw.get_wavelet("db4"), vw.BoundaryMode.PERIODIC, 4)      # bufferSize < L
+    with pytest.raises(vw.InvalidArgumentException):
+        vw.MODWTStreamingTransform.createMultiLevel(vw.get_wavelet("db4"), vw.BoundaryMode.PERIODIC, 64, 0)
+    with pytest.raises(vw.InvalidSignalException):
+        vw.MODWTStreamingTransform.create(vw.get_wavelet("db4"), vw.BoundaryMode.PERIODIC).process([])

@@ -14,5 +14,6 @@ from .modwt import (MODWTResult, MODWTTransform, MODWTTransformFactory, MultiLev
                     SymmetricAlignmentStrategy)
 from .ops import WaveletOperations  # noqa: F401
 from .streaming import BatchStreamingMODWT  # noqa: F401
+from .streaming_core import InvalidStateException, MODWTStreamingTransform  # noqa: F401
 from .swt import VectorWaveSwtAdapter  # noqa: F401
 from .wavelets import BoundaryMode, Coiflet, Daubechies, Haar, Symlet, Wavelet, get_wavelet  # noqa: F401

@@ -15,6 +15,7 @@ class ErrorCode(enum.Enum):
     CFG_UNSUPPORTED_OPERATION = "CFG_001"
     CFG_UNSUPPORTED_BOUNDARY_MODE = "CFG_003"
     CFG_INVALID_DECOMPOSITION_LEVEL = "CFG_004"
+    STATE_CLOSED = "STATE_001"
     STATE_INVALID = "STATE_002"
 
 
