@@ -448,6 +448,24 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
     (void)pending_stage;
 }
 
+// MutableMultiLevelMODWTResult.applyThresholdToArray fused into the synthesis load (:97-118): one pass over a landed W tile
+// in shared memory, 16-byte accesses.  Out of line and register-light on purpose: the kernel's register count is the maximum
+// over its call graph, and an unrolled inlined pass pushed the short-filter kernels from 56 to 80 registers, which cost the
+// plain inverse an occupancy step (haar 0.153 -> 0.217 ms).
+__device__ __noinline__ void threshold_tile(double *wbuf, int tot, bool aligned16, const double *lam_ptr, int soft) {
+    const double lam = __ldg(lam_ptr);
+    const bool nonneg = !(lam < 0.0);
+    auto thr1 = [&](double c) { return nonneg ? vw_threshold_nonneg(c, lam, soft) : vw_threshold_value(c, lam, soft); };
+    double2 *w2 = reinterpret_cast<double2 *>(wbuf);
+    const int tid = threadIdx.x, nt = (int)blockDim.x;
+    const int n2 = aligned16 ? tot >> 1 : 0;       // odd buffer pitch (no bulk copies): scalar loop below
+    for (int i = tid; i < n2; i += nt) {
+        const double2 q = w2[i];
+        w2[i] = make_double2(thr1(q.x), thr1(q.y));
+    }
+    for (int i = 2 * n2 + tid; i < tot; i += nt) wbuf[i] = thr1(wbuf[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused synthesis (index rule t + k*d: PERIODIC, ZERO_PADDING, linear span)
 // ------------------------------------------------------------------------------------------------
@@ -496,7 +514,6 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
                    &bars[1 + slot], !have);
     };
     stage_w(top, top & 1);
-    const double lam = a.thr ? a.thr[a.thr_per_row ? b : 0] : 0.0;   // fetched under the first tile's flight
     if (a.use_tma) mbar_wait(&bars[0], 0);
     uint32_t wphase0 = 0, wphase1 = 0;
 
@@ -514,24 +531,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= 12) ? 3 : 2) k_fused_
         const double *cv = cur + (lev == top ? par_v : 0);
         const int in_ext = extent(lev);
         if (a.thr && have_w) {
-            // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the load (:97-118): one pass over the
-            // landed tile, 16-byte accesses, four independent pairs in flight per thread (the staging buffer starts
-            // 16-byte aligned; the parity sample in front of an odd start is thresholded too and never read)
-            const bool nonneg = !(lam < 0.0);
-            const int soft = a.thr_soft;
-            auto thr1 = [&](double c) { return nonneg ? vw_threshold_nonneg(c, lam, soft) : vw_threshold_value(c, lam, soft); };
-            double2 *w2 = reinterpret_cast<double2 *>(slot ? wb1 : wb0);
-            const int tot = in_ext + par_w, nt = (int)blockDim.x;
-            const int n2 = (P & 1) ? 0 : tot >> 1;     // odd buffer pitch (no bulk copies): scalar loop below
-            for (int i = tid; i < n2; i += 4 * nt) {
-                double2 q[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) if (i + k * nt < n2) q[k] = w2[i + k * nt];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (i + k * nt < n2) w2[i + k * nt] = make_double2(thr1(q[k].x), thr1(q[k].y));
-            }
-            for (int i = 2 * n2 + tid; i < tot; i += nt) { double *wl = reinterpret_cast<double *>(w2) + i; *wl = thr1(*wl); }
+            threshold_tile(slot ? wb1 : wb0, in_ext + par_w, (P & 1) == 0, a.thr + (a.thr_per_row ? b : 0), a.thr_soft);
             __syncthreads();
         }
         const int ld2 = a.log2d0 + lev;
@@ -625,8 +625,11 @@ namespace {
 // Threads per CTA.  Long filters run register-heavy item loops (2 CTAs of 256 threads per SM at most): 128-thread CTAs
 // put 4 independent tiles on an SM instead, whose load / compute / store phases overlap far better (coif5 fused
 // levels: 1.76 -> 1.3 ms per level; sym8 / db8 +3..5 %); short filters keep 256.
-int launch_threads(const vw_ctx *ctx, int l) {
+// The 16..20-tap synthesis (four buffers per tile, at most 3 tiles per SM) does best in between: 192 threads
+// (db8 J = 6 N = 2^20 inverse 6.32 -> 5.95 ms; 128 and 256 are both slower).
+int launch_threads(const vw_ctx *ctx, int l, bool fwd) {
     if (ctx->opt_threads > 0) return (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31;
+    if (l >= 16 && l < 24 && !fwd) return 192;
     return l >= 16 ? 128 : kThreads;
 }
 
@@ -640,7 +643,7 @@ size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
 double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t t) {
-    const int nthreads = launch_threads(ctx, l);
+    const int nthreads = launch_threads(ctx, l, fwd);
     const int64_t d0 = 1ll << (first - 1);
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
@@ -781,7 +784,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = launch_threads(ctx, p.l);
+    const int nthreads = launch_threads(ctx, p.l, true);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);
 #define VW_FWD_CALL(LL, QQ)                                                                \
@@ -841,7 +844,7 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = launch_threads(ctx, p.l);
+    const int nthreads = launch_threads(ctx, p.l, false);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);   // on the arrays as the kernel sees them (reversed streams differ)
 #define VW_INV_CALL(LL, QQ)                                                                \
