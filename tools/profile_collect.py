@@ -80,3 +80,10 @@ for tag, title in ((f"prof_{R}_bench", "default bench workload (4096 x 4096, db4
                 break
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 print("profiles/:", sorted(os.listdir(P)))
+
+# ---- 4. plain copies: the bench lines and the per-config table ------------------------------------------------
+import shutil
+for src, dst in ((f"bench_{R}.json", f"{R}_bench_line.json"), (f"bench_ref_{R}.json", f"{R}_bench_reference_line.json"),
+                 (f"results_{R}.jsonl", f"{R}_config_results.jsonl")):
+    if os.path.exists(os.path.join(G, src)):
+        shutil.copyfile(os.path.join(G, src), os.path.join(P, dst))

@@ -630,9 +630,10 @@ namespace {
 // levels: 1.76 -> 1.3 ms per level; sym8 / db8 +3..5 %); short filters keep 256.
 // The 16..20-tap synthesis (four buffers per tile, at most 3 tiles per SM) does best in between: 192 threads
 // (db8 J = 6 N = 2^20 inverse 6.32 -> 5.95 ms; 128 and 256 are both slower).
-int launch_threads(const vw_ctx *ctx, int l, bool fwd) {
+// Single-level synthesis stages (the aligned SYMMETRIC ones) keep 128 (db8 SYMMETRIC inverse 7.05 vs 7.26 ms).
+int launch_threads(const vw_ctx *ctx, int l, bool fwd, int nlev) {
     if (ctx->opt_threads > 0) return (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31;
-    if (l >= 16 && l < 24 && !fwd) return 192;
+    if (l >= 16 && l < 24 && !fwd && nlev >= 2) return 192;
     return l >= 16 ? 128 : kThreads;
 }
 
@@ -646,7 +647,7 @@ size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
 double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t t) {
-    const int nthreads = launch_threads(ctx, l, fwd);
+    const int nthreads = launch_threads(ctx, l, fwd, nf);
     const int64_t d0 = 1ll << (first - 1);
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
@@ -789,7 +790,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = launch_threads(ctx, p.l, true);
+    const int nthreads = launch_threads(ctx, p.l, true, p.nlevels);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);
 #define VW_FWD_CALL(LL, QQ)                                                                \
@@ -849,7 +850,7 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
-    const int nthreads = launch_threads(ctx, p.l, false);
+    const int nthreads = launch_threads(ctx, p.l, false, p.nlevels);
     int rc = VW_OK;
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, p.l);   // on the arrays as the kernel sees them (reversed streams differ)
 #define VW_INV_CALL(LL, QQ)                                                                \
