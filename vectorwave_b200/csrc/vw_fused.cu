@@ -283,12 +283,22 @@ __device__ __forceinline__ void synthesis_item_dyn(const double *__restrict__ in
 // ------------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
+// L2 prefetch of [p, p + count) doubles clipped to the row [0, n): the future CTA's bulk copy then hits L2 instead of
+// queueing behind the stores in HBM (16-byte units; the rows are 16-byte aligned whenever the bulk path is on)
+__device__ __forceinline__ void prefetch_l2_span(const double *row, long long p, int count, long long n) {
+    long long lo = p < 0 ? 0 : p, hi = p + count > n ? n : p + count;
+    lo = (lo + 1) & ~1ll; hi &= ~1ll;
+    if (hi > lo)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row + lo), "r"((uint32_t)((hi - lo) * 8)) : "memory");
+}
+
 struct FwdArgs {
     const double *x; long long ldx;
     double *w; long long ldw, lsw;
     double *v; long long ldv;
     long long n_in, t0, n_out, batch;
     int tile, htot, slack, nlev, log2d0, mode, tiles_per_row, use_tma, use_stage, lrt;
+    int pf_dist;   // > 0: prefetch into L2 the input tile of the CTA `pf_dist` launches ahead (the one that takes this CTA's slot)
     VwFilt32 f;
 };
 
@@ -299,6 +309,7 @@ struct InvArgs {
     unsigned long long detail_mask;
     long long n_in, n_out, batch;
     int tile, htot, nlev, log2d0, mode, tiles_per_row, use_tma, lrt;
+    int pf_dist;   // as in FwdArgs: V and top-level W tiles of a future CTA
     const double *thr; int thr_per_row, thr_soft;
     long long off_v, off_w;   // stream offsets of an aligned single-level stage (SYMMETRIC sigma/tau); 0 otherwise
     VwFilt32 f;               // taps of a sigma = -1 stream arrive reversed
@@ -334,6 +345,13 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     if (a.use_tma && tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
     stage_tile(buf0, xrow, g0 - HT, PP, a.n_in, a.mode, a.use_tma, bar, false);
+    if (a.pf_dist > 0 && tid == 32) {
+        const long long fb = ((long long)blockIdx.x + a.pf_dist) / a.tiles_per_row;
+        if (fb < a.batch) {
+            const int ft = (int)(((long long)blockIdx.x + a.pf_dist) % a.tiles_per_row);
+            prefetch_l2_span(a.x + fb * a.ldx, a.t0 + (long long)ft * T - HT, P, a.n_in);
+        }
+    }
     if (a.use_tma) mbar_wait(bar, 0);
     __syncthreads();
 
@@ -517,6 +535,14 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
                    &bars[1 + slot], !have);
     };
     stage_w(top, top & 1);
+    if (a.pf_dist > 0 && tid == 32) {
+        const long long fb = ((long long)blockIdx.x + a.pf_dist) / a.tiles_per_row;
+        if (fb < a.batch) {
+            const long long fg = (long long)(((long long)blockIdx.x + a.pf_dist) % a.tiles_per_row) * T;
+            if (a.v) prefetch_l2_span(a.v + fb * a.ldv, fg + a.off_v, P, a.n_in);
+            if ((a.detail_mask >> top) & 1ull) prefetch_l2_span(a.w + (long long)top * a.lsw + fb * a.ldw, fg + a.off_w, P, a.n_in);
+        }
+    }
     if (a.use_tma) mbar_wait(&bars[0], 0);
     uint32_t wphase0 = 0, wphase1 = 0;
 
@@ -635,6 +661,22 @@ int launch_threads(const vw_ctx *ctx, int l, bool fwd, int nlev) {
     if (ctx->opt_threads > 0) return (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31;
     if (l >= 16 && l < 24 && !fwd && nlev >= 2) return 192;
     return l >= 16 ? 128 : kThreads;
+}
+
+// How many launches ahead a CTA prefetches (L2) the input tile of the CTA that will take over its slot: the number of
+// CTAs resident at once.  0 = off (everything resident, no bulk path, or vw_set_option("l2pf", 0)).
+int prefetch_distance(vw_ctx *ctx, const void *func, int nthreads, size_t smem, bool use_tma, unsigned grid) {
+    if (ctx->opt_l2pf <= 0 || !use_tma) return 0;
+    int per_sm = 0;
+    for (const auto &e : ctx->occ_cache)
+        if (e.func == func && e.nthreads == nthreads && e.smem == smem) per_sm = e.per_sm;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, nthreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        ctx->occ_cache.push_back({func, nthreads, smem, per_sm});
+    }
+    const long long resident = (long long)per_sm * ctx->sm_count;
+    if ((long long)grid <= resident) return 0;
+    return (int)std::min<long long>(resident, 1 << 30);
 }
 
 int64_t even_up(int64_t v) { return (v + 1) & ~1ll; }
@@ -796,6 +838,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
 #define VW_FWD_CALL(LL, QQ)                                                                \
     do {                                                                                   \
         if ((rc = set_smem(ctx, k_fused_analysis<LL, QQ>, smem))) return rc;               \
+        a.pf_dist = prefetch_distance(ctx, (const void *)k_fused_analysis<LL, QQ>, nthreads, smem, use_tma, grid); \
         k_fused_analysis<LL, QQ><<<grid, nthreads, smem, ctx->stream>>>(a);                \
     } while (0)
     VW_DISPATCH_L(p.l, qmf, VW_FWD_CALL)
@@ -856,6 +899,7 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
 #define VW_INV_CALL(LL, QQ)                                                                \
     do {                                                                                   \
         if ((rc = set_smem(ctx, k_fused_synthesis<LL, QQ>, smem))) return rc;              \
+        a.pf_dist = prefetch_distance(ctx, (const void *)k_fused_synthesis<LL, QQ>, nthreads, smem, use_tma, grid); \
         k_fused_synthesis<LL, QQ><<<grid, nthreads, smem, ctx->stream>>>(a);               \
     } while (0)
     VW_DISPATCH_L(p.l, qmf, VW_INV_CALL)

@@ -58,6 +58,9 @@ struct vw_ctx {
     int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
+    struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
+    std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
+    int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
     std::recursive_mutex mu;   // every public entry point holds it: calls on one ctx from several host threads serialise
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves

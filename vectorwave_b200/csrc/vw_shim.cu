@@ -482,6 +482,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "poly")) ctx->opt_poly = value;
     else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
     else if (!strcmp(name, "wave")) ctx->opt_wave = value;
+    else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
     return VW_OK;
