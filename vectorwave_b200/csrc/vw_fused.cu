@@ -440,17 +440,17 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
             __syncthreads();
         }
         if (staged) {
+            // a group has at most two staged levels (dilation 1 and 2) and each owns a staging buffer, so nothing is ever
+            // written twice: no wait, no barrier -- the bulk store drains while the next level computes
             if (a.use_tma) {
                 if (tid == 0) {
                     bulk_s2g(wrow, stg, (uint32_t)Tt * 8u);
                     bulk_commit();
                     pending_stage++;
-                    bulk_wait_read<1>();  // the other staging buffer is free again before anyone writes it
                 }
             } else {
                 for (int i = tid; i < Tt; i += (int)blockDim.x) wrow[i] = stg[i];
             }
-            __syncthreads();
         }
         double *t = cur; cur = nxt; nxt = t;
         lo_prev = lo_cur;
@@ -554,7 +554,9 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
             if (slot) { mbar_wait(&bars[2], wphase1); wphase1 ^= 1; }
             else { mbar_wait(&bars[1], wphase0); wphase0 ^= 1; }
         }
-        __syncthreads();
+        // hand-patched samples (padding, mirrors) of this level's tiles were written before the previous level's closing
+        // barrier; only the first level's were written just now.  Every thread polls the mbarrier itself for the bulk part.
+        if (lev == top || !a.use_tma) __syncthreads();
         const bool have_w = (a.detail_mask >> lev) & 1ull;
         double *wt = (slot ? wb1 : wb0) + par_w;
         const double *cv = cur + (lev == top ? par_v : 0);
