@@ -357,7 +357,6 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
 
     double *cur = buf0, *nxt = buf1;
     int lo_prev = 0;
-    int pending_stage = 0;  // bulk stores issued from staging buffers so far (thread 0 bookkeeping only)
     for (int lev = 0; lev < a.nlev; lev++) {
         const int ld2 = a.log2d0 + lev;
         const int d = 1 << ld2;
@@ -446,7 +445,6 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
                 if (tid == 0) {
                     bulk_s2g(wrow, stg, (uint32_t)Tt * 8u);
                     bulk_commit();
-                    pending_stage++;
                 }
             } else {
                 for (int i = tid; i < Tt; i += (int)blockDim.x) wrow[i] = stg[i];
@@ -466,7 +464,6 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     } else {
         for (int i = tid; i < Tt; i += (int)blockDim.x) vrow[i] = cur[HT + i];
     }
-    (void)pending_stage;
 }
 
 // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the synthesis load (:97-118): one pass over a landed W tile
