@@ -8,6 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vectorwave_b200 as vw
 S = 1.0 / math.sqrt(2.0)
 eng = vw.Engine.get()
+for kv in filter(None, os.environ.get("VW_OPTS", "").split(",")):   # e.g. VW_OPTS=l2pf=0,tile=2048
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 wv = vw.get_wavelet("db4")
 hs, gs = wv.lowPassDecomposition() * S, wv.highPassDecomposition() * S
 n = 4096
