@@ -765,6 +765,8 @@ double group_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t
 }  // namespace
 
 int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out) {
+    for (const auto &e : ctx->plan_cache)
+        if (e.forward == forward && e.l == l && e.levels == levels && e.n == n) { out = e.groups; return VW_OK; }
     out.clear();
     // FP64-bound filters (l >= 24) gain nothing from sharing a launch -- the halo recompute only adds FMAs (measured on coif5)
     const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : 4);
@@ -792,6 +794,8 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
     }
     for (int at = levels; at > 0; at -= pick[at].nlev) out.push_back(pick[at]);
     std::reverse(out.begin(), out.end());   // ascending levels; the inverse walks it backwards
+    if (ctx->plan_cache.size() >= 32) ctx->plan_cache.erase(ctx->plan_cache.begin());
+    ctx->plan_cache.push_back({forward, l, levels, n, out});
     return VW_OK;
 }
 

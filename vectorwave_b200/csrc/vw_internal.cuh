@@ -41,6 +41,8 @@ inline bool vw_is_qmf(const double *h, const double *g, int l) {
         if (g[k] != ((k & 1) ? -h[l - 1 - k] : h[l - 1 - k])) return false;
     return true;
 }
+struct VwPlanGroup { int first, nlev; int64_t tile; double cost; };
+
 struct vw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -58,6 +60,8 @@ struct vw_ctx {
     int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
+    struct PlanEntry { bool forward; int l, levels; int64_t n; std::vector<VwPlanGroup> groups; };
+    mutable std::vector<PlanEntry> plan_cache;   // launch plans by shape (the planner costs 2-35 us); cleared by vw_set_option
     struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
     std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
     int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
@@ -132,7 +136,6 @@ struct VwFusedInv {
 // Level schedule: which consecutive levels share one fused launch and with which tile, from a small cost model
 // (FP64-pipe cycles incl. halo recompute and ragged rounds vs HBM bytes incl. halo re-reads, overlapped across the
 // CTAs that fit one SM).  tile < 0 marks a level that only the per-level kernels can take.
-struct VwPlanGroup { int first, nlev; int64_t tile; double cost; };
 #include <vector>
 int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out);
 int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f);

@@ -476,6 +476,7 @@ int vw_device_index(const vw_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return VW_ENULL;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!strcmp(name, "tile")) ctx->opt_tile = value;
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;
     else if (!strcmp(name, "threads")) ctx->opt_threads = value;
@@ -485,6 +486,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
+    ctx->plan_cache.clear();   // plans depend on the knobs
     return VW_OK;
 }
 
