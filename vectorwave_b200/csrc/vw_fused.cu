@@ -622,10 +622,18 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
 // ------------------------------------------------------------------------------------------------
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int ilog2(int64_t v) { int r = 0; while ((1ll << r) < v) r++; return r; }
-
+// opt-in dynamic shared memory, raised once per kernel and size (the attribute is sticky; the call costs a microsecond)
 template <typename K>
 int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
+    const void *func = (const void *)kernel;
+    for (auto &e : ctx->smem_set)
+        if (e.first == func) {
+            if (e.second >= bytes) return VW_OK;
+            e.second = bytes;
+            return vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                                 "cudaFuncSetAttribute(max dynamic smem)");
+        }
+    ctx->smem_set.push_back({func, bytes});
     return vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                          "cudaFuncSetAttribute(max dynamic smem)");
 }

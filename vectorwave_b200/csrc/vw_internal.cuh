@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "vw_modwt.h"
@@ -62,6 +63,7 @@ struct vw_ctx {
     size_t pinned_bytes = 0;
     struct PlanEntry { bool forward; int l, levels; int64_t n; std::vector<VwPlanGroup> groups; };
     mutable std::vector<PlanEntry> plan_cache;   // launch plans by shape (the planner costs 2-35 us); cleared by vw_set_option
+    std::vector<std::pair<const void *, size_t>> smem_set;   // dynamic shared memory already opted in, per kernel
     struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
     std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
     int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
