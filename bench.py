@@ -381,7 +381,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "round_trip_max_abs_err": rt,
                 "roofline_model_gsamples": peak / (48.0 * levels),
-                "frac_of_roofline_model": value / world / (peak / (48.0 * levels))}
+                "frac_of_roofline_model": value / world / (peak / (48.0 * levels)),
+                "gsample_levels_per_s": value * 2.0 * levels}      # 2*J*B*N / t
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
