@@ -117,9 +117,9 @@ int check_finite(vw_ctx *ctx, const double *x_dev, int64_t batch, int64_t n, int
     int rc = vw_scratch(ctx, 5, 64, &cnt);
     if (rc) return rc;
     if ((rc = pinned_mailbox(ctx, 64, &mb))) return rc;
-    cudaMemsetAsync(cnt, 0, 8, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemsetAsync(cnt, 0, 8, ctx->stream), "small copy"))) return rc;
     if ((rc = vw_launch_nonfinite_count(ctx, x_dev, batch, n, ld, (unsigned long long *)cnt))) return rc;
-    cudaMemcpyAsync(mb, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(mb, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "finite check"))) return rc;
     unsigned long long bad = *(unsigned long long *)mb;
     if (bad) return vw_fail(ctx, VW_ENONFINITE, "%s contains %llu non-finite value(s) (NaN or Infinity)", what, bad);
@@ -591,13 +591,13 @@ int vw_conv_modwt(vw_ctx *ctx, const double *x, int64_t n, const double *filter,
         void *p;
         if ((rc = vw_scratch(ctx, 2, (size_t)(2 * n + lf) * 8, &p))) return rc;
         double *base = (double *)p;
-        cudaMemcpyAsync(base, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(base + 2 * n, filter, (size_t)lf * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(base, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream), "small copy"))) return rc;
+        if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(base + 2 * n, filter, (size_t)lf * 8, cudaMemcpyHostToDevice, ctx->stream), "small copy"))) return rc;
         xd = base; od = base + n; fd = base + 2 * n;
     }
     if (flags & VW_FLAG_CHECK_FINITE) if ((rc = check_finite(ctx, xd, 1, n, n, "signal"))) return rc;
     if ((rc = vw_launch_conv_dense(ctx, xd, n, fd, lf, mode, od, flags & VW_FLAG_BITEXACT))) return rc;
-    if (!dev) cudaMemcpyAsync(out, od, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!dev && (rc = vw_cuda_check(ctx, cudaMemcpyAsync(out, od, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     return finish(ctx, flags, !dev);
 }
 
@@ -766,7 +766,7 @@ int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t 
     if ((rc = vw_scratch(ctx, 5, (size_t)nthr * 8 + 64, &pt))) return rc;
     double *thr_dev = (double *)((char *)pt + 64);
     // thresholds are always read from the host (they come from vw_universal_threshold or the caller)
-    cudaMemcpyAsync(thr_dev, thresholds, (size_t)nthr * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(thr_dev, thresholds, (size_t)nthr * 8, cudaMemcpyHostToDevice, ctx->stream), "small copy"))) return rc;
     double *cd = coeffs;
     if (!dev) {
         void *p;
@@ -800,7 +800,7 @@ int vw_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t
     if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pt))) return rc;
     double *thr_dev = (double *)((char *)pt + 64);
     if ((rc = vw_launch_universal_threshold(ctx, wd, batch, n, ldd, thr_dev))) return rc;
-    cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "universal threshold");
 }
 
@@ -840,7 +840,7 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
         per_row = 1;
         if ((rc = vw_launch_universal_threshold(ctx, wd, batch, n, n, thr_dev))) return rc;
     } else {
-        cudaMemcpyAsync(thr_dev, &threshold, 8, cudaMemcpyHostToDevice, ctx->stream);
+        if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(thr_dev, &threshold, 8, cudaMemcpyHostToDevice, ctx->stream), "small copy"))) return rc;
         cudaStreamSynchronize(ctx->stream);  // &threshold is a stack address
     }
     // reconstruct; the thresholding rides on the synthesis: fused stages threshold W while it sits in shared memory
@@ -851,8 +851,11 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
                              ldod, flags, thr_dev, per_row, soft))) return rc;
     if (!dev) if ((rc = copy_rows(ctx, out, ldo, od, n, n, batch, cudaMemcpyDeviceToHost))) return rc;
     if (thresholds_out) {
-        if (per_row) cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        else for (int64_t b = 0; b < batch; b++) thresholds_out[b] = threshold;
+        if (per_row) {
+            if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(thresholds_out, thr_dev, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
+        } else {
+            for (int64_t b = 0; b < batch; b++) thresholds_out[b] = threshold;
+        }
     }
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "denoise");
 }
@@ -875,7 +878,7 @@ int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_
     if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pt))) return rc;
     double *med = (double *)((char *)pt + 64);
     if ((rc = vw_launch_median_abs(ctx, cd, batch, n, ldd, med))) return rc;
-    cudaMemcpyAsync(out, med, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(out, med, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "median");
 }
 
@@ -898,8 +901,8 @@ int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int
     if ((rc = vw_scratch(ctx, 5, (size_t)batch * 16 + 64, &pt))) return rc;
     double *md = (double *)((char *)pt + 64), *vd = md + batch;
     if ((rc = vw_launch_mean_variance(ctx, cd, batch, n, ldd, md, vd))) return rc;
-    cudaMemcpyAsync(mean_out, md, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(var_out, vd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(mean_out, md, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(var_out, vd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "mean/variance");
 }
 
@@ -928,8 +931,8 @@ int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, in
     if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(sd, sigma, (size_t)batch * 8, cudaMemcpyHostToDevice, ctx->stream), "sigma copy")))
         return rc;
     if ((rc = vw_launch_sure(ctx, cd, batch, n, ldd, sd, ws, td, rd))) return rc;
-    cudaMemcpyAsync(thr_out, td, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (risk_out) cudaMemcpyAsync(risk_out, rd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(thr_out, td, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
+    if (risk_out && (rc = vw_cuda_check(ctx, cudaMemcpyAsync(risk_out, rd, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     if ((rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "sure"))) return rc;
     const double root = sqrt(2.0 * log((double)n));
     for (int64_t b = 0; b < batch; b++) {                           // :465-469 compare with the universal threshold
@@ -958,7 +961,7 @@ int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld
     if ((rc = vw_scratch(ctx, 5, (size_t)batch * 8 + 64, &pe))) return rc;
     double *ed = (double *)((char *)pe + 64);
     if ((rc = vw_launch_energy(ctx, cd, batch, n, ldd, ed))) return rc;
-    cudaMemcpyAsync(out, ed, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((rc = vw_cuda_check(ctx, cudaMemcpyAsync(out, ed, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream), "small copy"))) return rc;
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "energy");
 }
 
