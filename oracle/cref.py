@@ -51,6 +51,8 @@ def lib():
         L.vwo_swt_denoise.argtypes = [_dp, _i64, _dp, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                       C.c_int, C.c_int, _dp]
         L.vwo_swt_denoise.restype = C.c_double
+        L.vwo_sure_threshold.argtypes = [_dp, _i64, C.c_double, _dp]
+        L.vwo_sure_threshold.restype = C.c_double
         L.vwo_batch_fwd_inv.argtypes = [_dp, _i64, _i64, _dp, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, _dp, _dp, _dp]
         L.vwo_batch_soa_decompose.argtypes = [_dp, _i64, _i64, _dp, _dp, _i64, C.c_int, _dp, _dp]
@@ -137,6 +139,14 @@ def threshold(c, thr, soft):
 def universal_threshold(w1):
     w1 = _c(w1)
     return lib().vwo_universal_threshold(_p(w1), w1.size)
+
+
+def sure_threshold(c, sigma):
+    """WaveletDenoiser.calculateSUREThreshold -> (threshold, minimal risk)"""
+    c = _c(c)
+    risk = np.empty(1)
+    thr = lib().vwo_sure_threshold(_p(c), c.size, float(sigma), _p(risk))
+    return thr, float(risk[0])
 
 
 def swt_denoise(x, h, g, levels, mode, wavelet_id=0, thr=-1.0, soft=True, dense=False):

@@ -331,6 +331,36 @@ double vwo_universal_threshold(const double *w1, int64_t n) {
     return sigma * sqrt(2 * log((double)n));
 }
 
+/* CORE/denoising/WaveletDenoiser.java:477-492 calculateSURERisk */
+static double sure_risk(const double *c, int64_t n, double threshold, double sigma) {
+    double sigma2 = sigma * sigma;
+    double risk = (double)(-n) * sigma2;
+    for (int64_t i = 0; i < n; i++) {
+        double a = fabs(c[i]);
+        if (a <= threshold) risk += c[i] * c[i];
+        else risk += sigma2 + (a - threshold) * (a - threshold);
+    }
+    return risk / (double)n;
+}
+
+/* CORE/denoising/WaveletDenoiser.java:441-472 calculateSUREThreshold: every sorted |c| is a candidate (the O(n^2) double
+ * loop), first strict minimum wins, capped at the universal threshold.  *min_risk_out (may be NULL) = the minimum. */
+double vwo_sure_threshold(const double *c, int64_t n, double sigma, double *min_risk_out) {
+    double *a = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; i++) a[i] = fabs(c[i]);
+    qsort(a, (size_t)n, sizeof(double), cmp_double);
+    double min_risk = INFINITY, best = 0.0;
+    for (int64_t k = 0; k < n; k++) {
+        double risk = sure_risk(c, n, a[k], sigma);
+        if (risk < min_risk) { min_risk = risk; best = a[k]; }
+    }
+    free(a);
+    double universal = sigma * sqrt(2.0 * log((double)n));
+    if (best > universal) best = universal;
+    if (min_risk_out) *min_risk_out = min_risk;
+    return best;
+}
+
 /* CORE/swt/VectorWaveSwtAdapter.java:546-562 denoise: decompose, threshold all detail
  * levels (thr<0 => universal), reconstruct.  Returns the threshold used. */
 double vwo_swt_denoise(const double *x, int64_t n, const double *h, const double *g, int64_t l,

@@ -3,7 +3,7 @@ against the numpy restatement of the reference."""
 import numpy as np
 import pytest
 
-from oracle import nptwin
+from oracle import cref, nptwin
 from oracle.javarandom import composite_sin
 from oracle.wavelets import filters
 
@@ -51,6 +51,9 @@ def test_oracle_sure_is_the_reference_double_loop():
              (np.array([1.0, -1.0, 1.0, 2.0, -2.0, 0.0, 0.0]), 0.7), (np.array([3.0]), 1.0), (np.zeros(5), 0.0)]
     for c, sigma in cases:
         assert nptwin.sure_threshold(c, sigma) == _sure_scalar(c, sigma)
+        assert cref.sure_threshold(c, sigma) == _sure_scalar(c, sigma)           # the C restatement, same loops
+    big = rng.standard_normal(3000) * np.where(rng.random(3000) < 0.05, 6.0, 1.0)
+    assert cref.sure_threshold(big, 1.0) == nptwin.sure_threshold(big, 1.0)
 
 
 @pytest.mark.gpu
