@@ -100,6 +100,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(props):
+    """Multi-rank runs: keep this process (and the pinned host buffers it first-touches) on the NUMA node the GPU hangs
+    off, so eight ranks do not push their PCIe traffic across the socket link.  Best effort: silently does nothing when
+    sysfs does not say (containers, single-node hosts)."""
+    try:
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -223,6 +245,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the MODWT engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_near_gpu(torch.cuda.get_device_properties(local_rank)) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -360,12 +383,12 @@ def main():
                "h2d_bytes_per_step": int((levels + 2) * eb * n * 8), "d2h_bytes_per_step": int((levels + 2) * eb * n * 8),
                "api": "Engine.forward/inverse with HOST (pinned) buffers == vw_modwt_forward / vw_modwt_inverse without "
                       "VW_FLAG_DEVICE_PTRS; coefficients cross PCIe both ways like the Java double[] API",
-               "batch": eb, "steps": esteps}
+               "batch": eb, "steps": esteps, "numa_node_bound": numa_node}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_port(args.workload, os.cpu_count() or 1)
+            cpu = cpu_port(args.workload, len(os.sched_getaffinity(0)) or 1)
             cpu["variants"] = cpu_variants(args.workload)
         except Exception as ex:  # the checker must never take the bench down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
