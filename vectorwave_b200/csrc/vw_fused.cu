@@ -292,6 +292,31 @@ __device__ __forceinline__ void prefetch_l2_span(const double *row, long long p,
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row + lo), "r"((uint32_t)((hi - lo) * 8)) : "memory");
 }
 
+// Developer instrumentation (make EXTRA=-DVW_PHASE_CLOCKS): thread 0 of every analysis CTA stamps %globaltimer (ns) at its
+// phase boundaries -- [0] start, [1] input tile landed, [2 + lev] level done, [7] last bulk store read out -- plus the SM
+// id in [6]; tools/phase_clocks.py reads the log through vw_debug_phase_log and reports where a tile's lifetime goes.
+#ifdef VW_PHASE_CLOCKS
+constexpr int kPhaseSlots = 8, kPhaseCtas = 16384;
+__device__ unsigned long long g_phase_log[kPhaseCtas * kPhaseSlots];
+__device__ __forceinline__ void phase_stamp(int slot) {
+    if (threadIdx.x == 0 && blockIdx.x < kPhaseCtas) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_phase_log[blockIdx.x * kPhaseSlots + slot] = t;
+    }
+}
+__device__ __forceinline__ void phase_smid() {
+    if (threadIdx.x == 0 && blockIdx.x < kPhaseCtas) {
+        unsigned int s;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+        g_phase_log[blockIdx.x * kPhaseSlots + 6] = s;
+    }
+}
+#define VW_PHASE(slot) phase_stamp(slot)
+#else
+#define VW_PHASE(slot) ((void)0)
+#endif
+
 struct FwdArgs {
     const double *x; long long ldx;
     double *w; long long ldw, lsw;
@@ -342,6 +367,10 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     const int PP = HT + Tt;                                      // valid extent of the tile buffers
     const double *xrow = a.x + b * a.ldx;
 
+    VW_PHASE(0);
+#ifdef VW_PHASE_CLOCKS
+    phase_smid();
+#endif
     if (a.use_tma && tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
     stage_tile(buf0, xrow, g0 - HT, PP, a.n_in, a.mode, a.use_tma, bar, false);
@@ -354,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     }
     if (a.use_tma) mbar_wait(bar, 0);
     __syncthreads();
+    VW_PHASE(1);
 
     double *cur = buf0, *nxt = buf1;
     int lo_prev = 0;
@@ -452,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
         }
         double *t = cur; cur = nxt; nxt = t;
         lo_prev = lo_cur;
+        if (lev < 4) VW_PHASE(2 + lev);
     }
     // V after the last level sits in cur[HT .. HT+Tt)
     double *vrow = a.v + b * a.ldv + (g0 - a.t0);
@@ -464,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     } else {
         for (int i = tid; i < Tt; i += (int)blockDim.x) vrow[i] = cur[HT + i];
     }
+    VW_PHASE(7);
 }
 
 // MutableMultiLevelMODWTResult.applyThresholdToArray fused into the synthesis load (:97-118): one pass over a landed W tile
@@ -918,3 +950,12 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "fused synthesis launch");
 }
+
+#ifdef VW_PHASE_CLOCKS
+// developer builds only: copies the phase log of the last analysis launch (count = CTAs x 8 words) to the host
+extern "C" __attribute__((visibility("default"))) int vw_debug_phase_log(unsigned long long *out, int ctas) {
+    if (ctas > kPhaseCtas) ctas = kPhaseCtas;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_phase_log, sizeof(unsigned long long) * (size_t)ctas * kPhaseSlots);
+}
+#endif
