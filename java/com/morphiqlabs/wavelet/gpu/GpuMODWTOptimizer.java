@@ -138,6 +138,31 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
         }
     }
 
+    /** BatchSIMDMODWT.batchMultiLevelMODWTSoA (extensions/modwt/BatchSIMDMODWT.java:343-381) on the caller's SoA arrays
+     *  ([t * batchSize + b]); levels == 1 with the literal Haar taps is batchMODWTSoA (:64-81).  No AoS round trip. */
+    public void batchMultiLevelMODWTSoA(double[] soaSignals, double[][] soaDetailPerLevel, double[] soaApproxOut,
+                                        Wavelet wavelet, int batchSize, int signalLength, int levels) {
+        if (soaDetailPerLevel.length != levels) throw new IllegalArgumentException("soaDetailPerLevel length must equal levels");
+        long tot = (long) batchSize * signalLength;
+        double[] hs = scaled(wavelet.lowPassDecomposition()), gs = scaled(wavelet.highPassDecomposition());
+        MemorySegment x = VwNative.allocPinned(tot * 8), out = VwNative.allocPinned(tot * 8 * (levels + 1));
+        try (Arena a = Arena.ofConfined()) {
+            VwNative.copyIn(x, soaSignals);
+            MemorySegment hseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, hs), gseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, gs);
+            MemorySegment ptrs = a.allocate(ValueLayout.ADDRESS, levels);
+            for (int j = 0; j < levels; j++) ptrs.setAtIndex(ValueLayout.ADDRESS, j, out.asSlice((long) j * tot * 8, tot * 8));
+            check((int) VwNative.vw_modwt_forward_soa.invokeExact(ctx, x, (long) batchSize, (long) signalLength, hseg, gseg,
+                    hs.length, levels, ptrs, out.asSlice((long) levels * tot * 8, tot * 8), 0));
+            for (int j = 0; j < levels; j++)
+                MemorySegment.copy(out, ValueLayout.JAVA_DOUBLE, (long) j * tot * 8, soaDetailPerLevel[j], 0, (int) tot);
+            MemorySegment.copy(out, ValueLayout.JAVA_DOUBLE, (long) levels * tot * 8, soaApproxOut, 0, (int) tot);
+        } catch (Throwable t) {
+            throw VwNative.rethrow(t);
+        } finally {
+            VwNative.freePinned(x); VwNative.freePinned(out);
+        }
+    }
+
     @Override
     public void close() {
         try {
