@@ -315,9 +315,23 @@ __device__ __forceinline__ void phase_smid() {
         g_phase_log[blockIdx.x * kPhaseSlots + 6] = s;
     }
 }
+// synthesis log, 16 words per CTA: [0] start, [1] V tile landed, level k of the launch (k = 0 first computed): [2 + 2k] its
+// W tile landed, [3 + 2k] level done; [10] SM id, [11] output bulk store read out
+constexpr int kPhaseSlotsInv = 16;
+__device__ unsigned long long g_phase_log_inv[kPhaseCtas * kPhaseSlotsInv];
+__device__ __forceinline__ void phase_stamp_inv(int slot) {
+    if (threadIdx.x == 0 && blockIdx.x < kPhaseCtas) {
+        unsigned long long t;
+        if (slot == 10) { unsigned int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); t = s; }
+        else asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_phase_log_inv[blockIdx.x * kPhaseSlotsInv + slot] = t;
+    }
+}
 #define VW_PHASE(slot) phase_stamp(slot)
+#define VW_PHASE_INV(slot) phase_stamp_inv(slot)
 #else
 #define VW_PHASE(slot) ((void)0)
+#define VW_PHASE_INV(slot) ((void)0)
 #endif
 
 struct FwdArgs {
@@ -587,6 +601,8 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     long long rem = a.n_out - g0;
     const int Tt = (int)(rem < T ? rem : T);
 
+    VW_PHASE_INV(0);
+    VW_PHASE_INV(10);
     if (a.use_tma && tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         mbar_fence_init();
@@ -620,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
         }
     }
     if (a.use_tma) mbar_wait(&bars[0], 0);
+    VW_PHASE_INV(1);
     uint32_t wphase0 = 0, wphase1 = 0;
 
     double *cur = buf0, *nxt = buf1;
@@ -633,6 +650,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
         // hand-patched samples (padding, mirrors) of this level's tiles were written before the previous level's closing
         // barrier; only the first level's were written just now.  Every thread polls the mbarrier itself for the bulk part.
         if (lev == top || !a.use_tma) __syncthreads();
+        if (top - lev < 4) VW_PHASE_INV(2 + 2 * (top - lev));
         const bool have_w = (a.detail_mask >> lev) & 1ull;
         double *wt = (slot ? wb1 : wb0) + par_w;
         const double *cv = cur + (lev == top ? par_v : 0);
@@ -682,6 +700,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
         }
         fence_async_smem();   // order this level's generic-proxy traffic before later bulk copies touch the buffers
         __syncthreads();
+        if (top - lev < 4) VW_PHASE_INV(3 + 2 * (top - lev));
         double *t = cur; cur = nxt; nxt = t;
     }
     double *orow = a.out + b * a.ldo + g0;
@@ -694,6 +713,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     } else {
         for (int i = tid; i < Tt; i += (int)blockDim.x) orow[i] = cur[i];
     }
+    VW_PHASE_INV(11);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1004,5 +1024,10 @@ extern "C" __attribute__((visibility("default"))) int vw_debug_phase_log(unsigne
     if (ctas > kPhaseCtas) ctas = kPhaseCtas;
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, g_phase_log, sizeof(unsigned long long) * (size_t)ctas * kPhaseSlots);
+}
+extern "C" __attribute__((visibility("default"))) int vw_debug_phase_log_inv(unsigned long long *out, int ctas) {
+    if (ctas > kPhaseCtas) ctas = kPhaseCtas;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_phase_log_inv, sizeof(unsigned long long) * (size_t)ctas * kPhaseSlotsInv);
 }
 #endif
