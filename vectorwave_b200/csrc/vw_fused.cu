@@ -30,7 +30,13 @@ namespace {
 #ifndef VW_LB4_MAXL
 #define VW_LB4_MAXL 0   // filters up to this length are compiled for 4 CTAs of 256 threads per SM (64 registers)
 #endif
-constexpr int kR = 9;          // outputs per thread item (odd => conflict-free strided LDS.64)
+#ifndef VW_KR
+#define VW_KR 9
+#endif
+#ifndef VW_STAGE_W
+#define VW_STAGE_W 1   // 0 (developer builds): detail rows of dilation 1 / 2 leave straight from registers instead of smem + bulk store
+#endif
+constexpr int kR = VW_KR;          // outputs per thread item (odd => conflict-free strided LDS.64)
 constexpr int kThreads = 256;  // maximum threads per CTA (launch bound); the launch may use fewer
 
 // ------------------------------------------------------------------------------------------------
@@ -799,7 +805,7 @@ double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t 
     const int64_t d0 = 1ll << (first - 1);
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
-    const bool use_stage = fwd && d0 < 4;
+    const bool use_stage = fwd && d0 < 4 && VW_STAGE_W;
     const size_t smem = smem_bytes(fwd, t, htot, use_stage);
     if (smem > ctx->smem_optin - 1024) return INFINITY;
     const int regs = l <= VW_LB4_MAXL ? 64 : (l <= 12 ? 85 : 128);
@@ -913,7 +919,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     const int64_t htot = (hexact + 1) & ~1ll;
     if (hexact > p.n_in || htot > 24576) return VW_EUNSUPPORTED;
     if (p.first_level + p.nlevels - 1 > 30) return VW_EUNSUPPORTED;
-    const bool use_stage = d0 < 4;
+    const bool use_stage = d0 < 4 && VW_STAGE_W;
     const bool use_tma = aligned16(p.x) && aligned16(p.w) && aligned16(p.v) && !(p.ldx & 1) && !(p.ldw & 1) &&
                          !(p.lsw & 1) && !(p.ldv & 1) && !(p.n_in & 1) && !(p.t0 & 1) && !(p.n_out & 1);
     const size_t smem_cap = ctx->smem_optin - 1024;
