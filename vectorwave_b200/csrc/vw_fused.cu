@@ -33,6 +33,9 @@ namespace {
 #ifndef VW_KR
 #define VW_KR 9
 #endif
+#ifndef VW_FENCE_MIN
+#define VW_FENCE_MIN 0
+#endif
 #ifndef VW_STAGE_W
 #define VW_STAGE_W 1   // 0 (developer builds): detail rows of dilation 1 / 2 leave straight from registers instead of smem + bulk store
 #endif
@@ -524,7 +527,11 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
             }
         }
         }
+#if VW_FENCE_MIN   // developer builds: only the levels whose outputs a bulk store reads (staged W, the final V) need the proxy fence
+        if (staged || last) fence_async_smem();
+#else
         fence_async_smem();   // generic-proxy writes of nxt / stg must be visible to the bulk-store (async) proxy
+#endif
         __syncthreads();
         // SYMMETRIC: V_lev at positions < 0 is the mirror of V_lev itself (ScalarOps.java:818-835 applied per level)
         if (a.mode == VW_SYMMETRIC && !last && g0 - HT < 0) {
