@@ -45,7 +45,7 @@ extern "C" {
 #define VW_API
 #endif
 
-#define VW_ABI_VERSION 1
+#define VW_ABI_VERSION 2
 #define VW_MAX_FILTER_TAPS 128 /* coif17 = 102 taps is the reference's longest table */
 #define VW_MAX_LEVELS 32
 
@@ -258,6 +258,124 @@ VW_API int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels);
 VW_API int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t ldin, int64_t hist, int64_t n,
                           const double *hs, const double *gs, int32_t l, int32_t level, double *w, int64_t ldw,
                           double *v, int64_t ldv, uint32_t flags);
+
+/* ---- span-sharded long signals, whole cascade per rank (up-front halo schedule) ---------------------------- */
+/* The halo a rank needs is tiny next to its span ((l-1)*(2^levels-1) samples), so it is exchanged ONCE per direction:
+ * before the analysis every rank receives the last `lead` samples of its left neighbour's x; before the synthesis the
+ * first samples of its right neighbour's V_J and W_j rows (ring wrap for PERIODIC, zeros at the open ends for
+ * ZERO_PADDING).  Every level then runs on a region that shrinks by its own halo -- no per-level synchronisation.
+ * vw_span_plan_query gives the layout both directions share (pure host logic, no device needed):
+ *   x work row   [lead | n_local]                 (the halo lands in front of the span)
+ *   W rows       [lead_w | n_local | pad]          `levels` rows, row_stride >= lead_w + n_local + pad apart
+ *   V_J row      [n_local | pad]
+ * Halos are rounded up to 32 samples so every kernel sees sector-aligned rows.  Reference precedent for the halo
+ * semantics: EXT/extensions/modwt/BatchSIMDMODWT.java:447-507; NOT StructuredParallelTransform.forwardChunked
+ * (EXT/extensions/parallel/StructuredParallelTransform.java:313-341), which has no halo. */
+#define VW_SPAN_MAX_GROUPS 16
+typedef struct vw_span_plan {
+    int32_t l, levels, world, reserved;
+    int64_t n_local;
+    int32_t ngroups_f, ngroups_i;                       /* launch groups of the analysis / synthesis cascade */
+    int32_t first_f[VW_SPAN_MAX_GROUPS], nlev_f[VW_SPAN_MAX_GROUPS];
+    int32_t first_i[VW_SPAN_MAX_GROUPS], nlev_i[VW_SPAN_MAX_GROUPS];
+    int64_t halo_f[VW_SPAN_MAX_GROUPS], halo_i[VW_SPAN_MAX_GROUPS];   /* per group, rounded up to 32 samples */
+    int64_t lead;          /* left halo of x: sum of halo_f */
+    int64_t lead_w;        /* spare samples on the left of every W row: sum of halo_f[1..] */
+    int64_t pad;           /* spare samples on the right of V_J and of every W row: sum of halo_i */
+    int64_t inverse_msg;   /* doubles in one rank's synthesis halo message (vw_span_pack_inverse) */
+} vw_span_plan;
+/* VW_ELENGTH when the total halo exceeds n_local (use fewer ranks / levels, or the per-group calls above). */
+VW_API int vw_span_plan_query(int32_t l, int32_t levels, int64_t n_local, int32_t world, vw_span_plan *out);
+/* Analysis of one rank's span, all levels: xext = [lead | n_local] with the left neighbour's halo already in place.
+ * Writes W_j[span] at w + (j-1)*row_stride + lead_w (the lead_w samples before it are engine work space) and V_J[span]
+ * at v.  Device pointers only. */
+VW_API int vw_modwt_forward_span_all(vw_ctx *ctx, const double *xext, const vw_span_plan *plan, const double *hs,
+                              const double *gs, double *w, int64_t row_stride, double *v, uint32_t flags);
+/* The synthesis halo message of this rank: the first samples of V_J and of every W_j row its LEFT neighbour needs,
+ * gathered into `msg` (plan->inverse_msg doubles, device); unpack scatters a received message into the pad areas. */
+VW_API int vw_span_pack_inverse(vw_ctx *ctx, const vw_span_plan *plan, const double *w, int64_t row_stride, const double *v,
+                         double *msg, uint32_t flags);
+VW_API int vw_span_unpack_inverse(vw_ctx *ctx, const vw_span_plan *plan, const double *msg, double *w, int64_t row_stride,
+                           double *v, uint32_t flags);
+/* Synthesis of one rank's span, all levels, halos already in the pad areas.  xout: n_local doubles. */
+VW_API int vw_modwt_inverse_span_all(vw_ctx *ctx, const vw_span_plan *plan, const double *w, int64_t row_stride,
+                              const double *v, const double *hs, const double *gs, int32_t order, double *xout,
+                              uint32_t flags);
+
+/* ---- several GPUs driven by ONE host thread (the JVM case) ------------------------------------------------------ */
+/* vw_init_multi opens one ctx per listed device and enables peer access between ring neighbours.  The sharded calls
+ * take one DEVICE pointer per device (allocated with vw_device_alloc on vw_multi_ctx(m, r)), enqueue the halo
+ * exchange as peer copies over NVLink (cudaMemcpyPeerAsync; ring wrap for PERIODIC) and the per-device cascades on
+ * each device's own stream, and return when every device has finished (or right after enqueueing with
+ * VW_FLAG_NO_SYNC; vw_multi_synchronize then waits).  Batches need no such call: signals are independent, use one ctx
+ * per device.  SURVEY.md 8(b)/(e). */
+typedef struct vw_multi vw_multi;
+VW_API int vw_init_multi(const int *devices, int32_t ndev, vw_multi **out);
+VW_API int vw_destroy_multi(vw_multi *m);
+VW_API int32_t vw_multi_size(const vw_multi *m);
+VW_API vw_ctx *vw_multi_ctx(vw_multi *m, int32_t rank);
+VW_API const char *vw_multi_last_error(const vw_multi *m);
+VW_API int vw_multi_synchronize(vw_multi *m);
+/* xext[r]: [lead | n_local] on device r with the span filled (the engine fills the lead); w[r]: `levels` rows of
+ * row_stride; v[r]: [n_local | pad].  mode: VW_PERIODIC or VW_ZERO_PADDING.  exchange_ms (may be NULL): device time of
+ * the slowest halo copy, measured with events (forces a synchronise). */
+VW_API int vw_modwt_forward_sharded(vw_multi *m, const vw_span_plan *plan, double *const *xext, const double *hs,
+                             const double *gs, int32_t mode, double *const *w, int64_t row_stride, double *const *v,
+                             float *exchange_ms, uint32_t flags);
+VW_API int vw_modwt_inverse_sharded(vw_multi *m, const vw_span_plan *plan, double *const *w, int64_t row_stride,
+                             double *const *v, const double *hs, const double *gs, int32_t mode, int32_t order,
+                             double *const *xout, float *exchange_ms, uint32_t flags);
+
+/* ---- device-resident results (MultiLevelMODWTResult kept on the GPU between calls) ------------------------------ */
+/* CORE/modwt/MultiLevelMODWTResultImpl.java:51-139 and MutableMultiLevelMODWTResultImpl are opaque enough to be backed
+ * by device memory: decompose once, threshold / measure / reconstruct without the coefficients ever crossing PCIe; a
+ * level is copied to the host only when the caller asks for it (getDetailCoeffsAtLevel -> vw_result_get_level).
+ * A decompose -> threshold -> reconstruct pipeline then moves 16 B/sample over PCIe instead of 16*(levels+2). */
+typedef struct vw_result vw_result;
+/* x: host (staged) or device pointer per flags.  *res == NULL: a new result is allocated; otherwise *res is reused when
+ * its shape matches (no allocation on the steady state) and replaced when it does not. */
+VW_API int vw_modwt_decompose_h(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const double *hs,
+                         const double *gs, int32_t l, int32_t levels, int32_t mode, vw_result **res, uint32_t flags);
+VW_API int vw_result_shape(const vw_result *res, int64_t *batch, int64_t *n, int32_t *levels);
+/* level 1..levels: W_level; level 0: V_J.  dst: [batch][n] rows of stride ld; host unless VW_FLAG_DEVICE_PTRS. */
+VW_API int vw_result_get_level(vw_ctx *ctx, const vw_result *res, int32_t level, double *dst, int64_t ld, uint32_t flags);
+/* MutableMultiLevelMODWTResult.setDetailCoeffs / setApproximationCoeffs: overwrite one level from src. */
+VW_API int vw_result_set_level(vw_ctx *ctx, vw_result *res, int32_t level, const double *src, int64_t ld, uint32_t flags);
+/* zero-copy device view of one level (row stride n): for callers that keep working on the device */
+VW_API double *vw_result_device_ptr(const vw_result *res, int32_t level);
+/* MutableMultiLevelMODWTResult.applyThreshold on level `level` (1..levels), or on every detail level when level == 0;
+ * thresholds: 1 or (per_row) batch HOST values. */
+VW_API int vw_result_threshold(vw_ctx *ctx, vw_result *res, int32_t level, const double *thresholds, int32_t per_row,
+                        int32_t soft);
+/* VectorWaveSwtAdapter.applyUniversalThreshold: per-row universal threshold from W_1, applied to every detail level;
+ * thresholds_out (may be NULL): batch HOST doubles. */
+VW_API int vw_result_universal_threshold(vw_ctx *ctx, vw_result *res, int32_t soft, double *thresholds_out);
+/* getDetailEnergyAtLevel (level >= 1) / getApproximationEnergy (level 0): batch HOST doubles. */
+VW_API int vw_result_energy(vw_ctx *ctx, const vw_result *res, int32_t level, double *out);
+/* MultiLevelMODWTTransform.reconstruct / reconstructFromLevel / reconstructLevels from the resident coefficients. */
+VW_API int vw_modwt_reconstruct_h(vw_ctx *ctx, const vw_result *res, const double *hs, const double *gs, int32_t l,
+                           int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask, int32_t use_approx,
+                           double *xout, int64_t ldx, uint32_t flags);
+VW_API int vw_result_free(vw_ctx *ctx, vw_result *res);
+
+/* ---- replaying a fixed call sequence as one CUDA graph (small, latency-bound shapes) --------------------------- */
+/* Between vw_graph_begin and vw_graph_end every engine call on this ctx is captured instead of executed (calls must
+ * not need a device->host answer: no VW_FLAG_CHECK_FINITE, no threshold selectors; host buffers must be pinned and
+ * stay valid; run the same calls once un-captured first so the scratch buffers exist).  vw_graph_launch replays the
+ * whole sequence -- copies included -- with one launch.  Reference shape: config #1/#2's small transforms, which the
+ * JVM runs in 117-358 us (docs/BENCHMARK-RESULTS.md:26). */
+typedef struct vw_graph vw_graph;
+VW_API int vw_graph_begin(vw_ctx *ctx);
+VW_API int vw_graph_end(vw_ctx *ctx, vw_graph **out);
+VW_API int vw_graph_launch(vw_ctx *ctx, vw_graph *g, uint32_t flags);
+VW_API int vw_graph_destroy(vw_ctx *ctx, vw_graph *g);
+
+/* ---- timing of the last call ----------------------------------------------------------------- */
+/* With vw_set_option(ctx, "timing", 1) every public call brackets its device work with CUDA events; vw_last_timing
+ * reports the last call: device milliseconds (first enqueue to last), host milliseconds inside the call, kernels
+ * launched.  Also wraps each call in an NVTX range ("vw_modwt_forward", ...) visible to Nsight tools. */
+typedef struct vw_timing { float device_ms; float host_ms; int32_t launches; int32_t reserved; } vw_timing;
+VW_API int vw_last_timing(vw_ctx *ctx, vw_timing *out);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ def test_ctypes_table_matches_header():
 
 def test_pure_host_entry_points_work_without_a_gpu():
     lib = vw.load_library()
-    assert lib.vw_abi_version() == 1
+    assert lib.vw_abi_version() == 2
     assert lib.vw_max_levels(10000, 2, 10) == 9          # CTEST/modwt/MultiLevelMODWTTransformTest.java:275
     assert lib.vw_max_levels(10000, 2, 0) == 14
     assert lib.vw_max_levels(8, 8, 10) == 0

@@ -1,0 +1,9 @@
+# lean tile kernels: correctness (whole GPU suite) and A/B against the general kernels on one box
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for rep in 1 2; do for lean in 0 3; do
+  python tools/quickbench.py --configs c2_haar,c2_db4,c3_sym8,c5_db8 --reps 20 --lean $lean | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print('lean $lean', d['config'], d['fwd_ms'], d['inv_ms'], d['fwdinv_gsamples'], d['fwd_launches'], d['inv_launches'], d['rt_err'])"
+done; done

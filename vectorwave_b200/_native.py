@@ -42,6 +42,23 @@ class VwAlign(C.Structure):
     _fields_ = [("sigma_h", C.c_int32), ("tau_h", C.c_int32), ("sigma_g", C.c_int32), ("tau_g", C.c_int32)]
 
 
+SPAN_MAX_GROUPS = 16
+
+
+class VwSpanPlan(C.Structure):
+    """vw_span_plan of include/vw_modwt.h: the layout and launch groups of a span-sharded cascade."""
+    _fields_ = [("l", C.c_int32), ("levels", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32),
+                ("n_local", C.c_int64), ("ngroups_f", C.c_int32), ("ngroups_i", C.c_int32),
+                ("first_f", C.c_int32 * SPAN_MAX_GROUPS), ("nlev_f", C.c_int32 * SPAN_MAX_GROUPS),
+                ("first_i", C.c_int32 * SPAN_MAX_GROUPS), ("nlev_i", C.c_int32 * SPAN_MAX_GROUPS),
+                ("halo_f", C.c_int64 * SPAN_MAX_GROUPS), ("halo_i", C.c_int64 * SPAN_MAX_GROUPS),
+                ("lead", C.c_int64), ("lead_w", C.c_int64), ("pad", C.c_int64), ("inverse_msg", C.c_int64)]
+
+
+class VwTiming(C.Structure):
+    _fields_ = [("device_ms", C.c_float), ("host_ms", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 _i64 = C.c_int64
@@ -88,6 +105,37 @@ SIGNATURES = {
     "vw_modwt_forward_span": (C.c_int, [_vp, _vp, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _vp, _i64, _vp, _u32]),
     "vw_modwt_inverse_span": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, _i32, _vp, _u32]),
     "vw_span_halo": (_i64, [_i32, _i32, _i32]),
+    "vw_span_plan_query": (C.c_int, [_i32, _i32, _i64, _i32, C.POINTER(VwSpanPlan)]),
+    "vw_modwt_forward_span_all": (C.c_int, [_vp, _vp, C.POINTER(VwSpanPlan), _dp, _dp, _vp, _i64, _vp, _u32]),
+    "vw_span_pack_inverse": (C.c_int, [_vp, C.POINTER(VwSpanPlan), _vp, _i64, _vp, _vp, _u32]),
+    "vw_span_unpack_inverse": (C.c_int, [_vp, C.POINTER(VwSpanPlan), _vp, _vp, _i64, _vp, _u32]),
+    "vw_modwt_inverse_span_all": (C.c_int, [_vp, C.POINTER(VwSpanPlan), _vp, _i64, _vp, _dp, _dp, _i32, _vp, _u32]),
+    "vw_init_multi": (C.c_int, [C.POINTER(C.c_int), _i32, C.POINTER(_vp)]),
+    "vw_destroy_multi": (C.c_int, [_vp]),
+    "vw_multi_size": (_i32, [_vp]),
+    "vw_multi_ctx": (_vp, [_vp, _i32]),
+    "vw_multi_last_error": (C.c_char_p, [_vp]),
+    "vw_multi_synchronize": (C.c_int, [_vp]),
+    "vw_modwt_forward_sharded": (C.c_int, [_vp, C.POINTER(VwSpanPlan), C.POINTER(_vp), _dp, _dp, _i32, C.POINTER(_vp), _i64,
+                                           C.POINTER(_vp), C.POINTER(C.c_float), _u32]),
+    "vw_modwt_inverse_sharded": (C.c_int, [_vp, C.POINTER(VwSpanPlan), C.POINTER(_vp), _i64, C.POINTER(_vp), _dp, _dp, _i32,
+                                           _i32, C.POINTER(_vp), C.POINTER(C.c_float), _u32]),
+    "vw_modwt_decompose_h": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _dp, _i32, _i32, _i32, C.POINTER(_vp), _u32]),
+    "vw_result_shape": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "vw_result_get_level": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _u32]),
+    "vw_result_set_level": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _u32]),
+    "vw_result_device_ptr": (_vp, [_vp, _i32]),
+    "vw_result_threshold": (C.c_int, [_vp, _vp, _i32, _dp, _i32, _i32]),
+    "vw_result_universal_threshold": (C.c_int, [_vp, _vp, _i32, _dp]),
+    "vw_result_energy": (C.c_int, [_vp, _vp, _i32, _dp]),
+    "vw_modwt_reconstruct_h": (C.c_int, [_vp, _vp, _dp, _dp, _i32, _i32, C.POINTER(VwAlign), _i32, C.c_uint64, _i32, _vp,
+                                         _i64, _u32]),
+    "vw_result_free": (C.c_int, [_vp, _vp]),
+    "vw_graph_begin": (C.c_int, [_vp]),
+    "vw_graph_end": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vw_graph_launch": (C.c_int, [_vp, _vp, _u32]),
+    "vw_graph_destroy": (C.c_int, [_vp, _vp]),
+    "vw_last_timing": (C.c_int, [_vp, C.POINTER(VwTiming)]),
 }
 
 _lib = None
@@ -208,7 +256,9 @@ class Engine:
         raise exc(f"{name}: {msg}")
 
     def _bind_stream(self, *arrays):
-        """device pointers => run on torch's current stream; returns the flag word."""
+        """device pointers => run on torch's current stream; returns the flag word.  Callers hold _call_lock across this and
+        the ABI call that follows: vw_set_stream + the launch are two calls, and another thread rebinding the ctx in
+        between would put the kernels on the wrong stream."""
         if any(_is_torch(a) for a in arrays if a is not None):
             import torch
             for a in arrays:
@@ -291,16 +341,16 @@ class Engine:
             import torch
             fdev = torch.as_tensor(filt, device=x2.device)
             res = out if out is not None else torch.empty_like(x2[0])
-            fl = self._bind_stream(x2, res) | flags
             with self._call_lock:
+                fl = self._bind_stream(x2, res) | flags
                 self._check(self.lib.vw_conv_modwt(self.ctx, _vp(x2.data_ptr()), x2.shape[1], _vp(fdev.data_ptr()),
                                                    filt.size, mode, _vp(res.data_ptr()), fl))
             return res
         res = out if out is not None else np.empty(x2.shape[1])
         if res.dtype != np.float64 or not res.flags.c_contiguous or res.size != x2.shape[1]:
             raise IllegalArgumentException("output must be a contiguous float64 array of the signal's length")
-        fl = self._bind_stream() | flags
         with self._call_lock:
+            fl = self._bind_stream() | flags
             self._check(self.lib.vw_conv_modwt(self.ctx, _vp(x2.ctypes.data), x2.shape[1], _vp(filt.ctypes.data),
                                                filt.size, mode, _vp(res.ctypes.data), fl))
         return res
@@ -315,10 +365,10 @@ class Engine:
         lev = max(int(levels), 0)
         w = w_out if w_out is not None else self._empty_like_rows(x2, max(lev, 1), b, max(n, 1))
         v = v_out if v_out is not None else self._empty_like_rows(x2, b, max(n, 1))
-        fl = self._bind_stream(x2, w, v) | flags
         ldw = w.stride(1) if _is_torch(w) else w.strides[1] // 8
         lsw = w.stride(0) if _is_torch(w) else w.strides[0] // 8
         with self._call_lock:
+            fl = self._bind_stream(x2, w, v) | flags
             self._check(self.lib.vw_modwt_forward(
                 self.ctx, _vp(_ptr(x2)), b, n, _ld(x2), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
                 int(levels), int(mode), _vp(_ptr(w)), ldw, lsw, _vp(_ptr(v)), _ld(v), fl))
@@ -340,9 +390,9 @@ class Engine:
                 (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous)
             if not ok or (a.numel() if _is_torch(a) else a.size) != tot:
                 raise IllegalArgumentException("SoA buffers must be contiguous float64 arrays of batchSize * signalLength")
-        fl = self._bind_stream(*arrs) | flags
         ptrs = (C.c_void_p * max(levels, 1))(*[_ptr(a) for a in soa_w_levels])
         with self._call_lock:
+            fl = self._bind_stream(*arrs) | flags
             self._check(self.lib.vw_modwt_forward_soa(
                 self.ctx, _vp(_ptr(soa_x)), int(batch), int(n), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
                 levels, ptrs, _vp(_ptr(soa_v)), fl))
@@ -370,9 +420,9 @@ class Engine:
         if detail_mask is None:
             detail_mask = (1 << levels) - 1
         res = out if out is not None else self._empty_like_rows(v, b, n)
-        fl = self._bind_stream(w, v, res) | flags
         al = self._align_array(align, levels)
         with self._call_lock:
+            fl = self._bind_stream(w, v, res) | flags
             self._check(self.lib.vw_modwt_inverse(
                 self.ctx, _vp(_ptr(w)), n, b * n, _vp(_ptr(v)), n, b, n, hs.ctypes.data_as(_dp),
                 gs.ctypes.data_as(_dp), hs.size, levels, int(mode), al, int(order), C.c_uint64(detail_mask),
@@ -388,8 +438,8 @@ class Engine:
             raise IllegalArgumentException("one threshold per row expected")
         if not _is_torch(c2) and not np.shares_memory(c2, coeffs):
             raise IllegalArgumentException("in-place thresholding needs a contiguous float64 array")
-        fl = self._bind_stream(c2) | flags
         with self._call_lock:
+            fl = self._bind_stream(c2) | flags
             self._check(self.lib.vw_threshold(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                               thr.ctypes.data_as(_dp), per_row, int(bool(soft)), fl))
         return coeffs
@@ -397,8 +447,8 @@ class Engine:
     def universal_threshold(self, w1, flags=0):
         w2, one_d = self._rows(w1, "coefficients")
         out = np.empty(w2.shape[0])
-        fl = self._bind_stream(w2) | flags
         with self._call_lock:
+            fl = self._bind_stream(w2) | flags
             self._check(self.lib.vw_universal_threshold(self.ctx, _vp(_ptr(w2)), w2.shape[0], w2.shape[1], _ld(w2),
                                                         out.ctypes.data_as(_dp), fl))
         return float(out[0]) if one_d else out
@@ -409,9 +459,9 @@ class Engine:
         hs, gs = _fp(hs), _fp(gs)
         res = self._empty_like_rows(x2, b, max(n, 1))
         thr = np.empty(max(b, 1))
-        fl = self._bind_stream(x2, res) | flags
         al = self._align_array(align, int(levels)) if align is not None else None
         with self._call_lock:
+            fl = self._bind_stream(x2, res) | flags
             self._check(self.lib.vw_swt_denoise(
                 self.ctx, _vp(_ptr(x2)), b, n, _ld(x2), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size,
                 int(levels), int(mode), al, int(order), float(threshold), int(bool(soft)), _vp(_ptr(res)), _ld(res),
@@ -422,8 +472,8 @@ class Engine:
         """exact median(|c|) per row (WaveletDenoiser.estimateNoiseSigma's order statistic)"""
         c2, one_d = self._rows(c, "coefficients")
         out = np.empty(c2.shape[0])
-        fl = self._bind_stream(c2) | flags
         with self._call_lock:
+            fl = self._bind_stream(c2) | flags
             self._check(self.lib.vw_median_abs(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                                out.ctypes.data_as(_dp), fl))
         return float(out[0]) if one_d else out
@@ -432,8 +482,8 @@ class Engine:
         """(mean, population variance about the mean) per row"""
         c2, one_d = self._rows(c, "coefficients")
         m, v = np.empty(c2.shape[0]), np.empty(c2.shape[0])
-        fl = self._bind_stream(c2) | flags
         with self._call_lock:
+            fl = self._bind_stream(c2) | flags
             self._check(self.lib.vw_mean_variance(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                                   m.ctypes.data_as(_dp), v.ctypes.data_as(_dp), fl))
         return (float(m[0]), float(v[0])) if one_d else (m, v)
@@ -443,8 +493,8 @@ class Engine:
         c2, one_d = self._rows(c, "coefficients")
         sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (c2.shape[0],)))
         thr, risk = np.empty(c2.shape[0]), np.empty(c2.shape[0])
-        fl = self._bind_stream(c2) | flags
         with self._call_lock:
+            fl = self._bind_stream(c2) | flags
             self._check(self.lib.vw_sure_threshold(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                                    sg.ctypes.data_as(_dp), thr.ctypes.data_as(_dp),
                                                    risk.ctypes.data_as(_dp), fl))
@@ -455,8 +505,8 @@ class Engine:
     def energy(self, c, flags=0):
         c2, one_d = self._rows(c, "coefficients")
         out = np.empty(c2.shape[0])
-        fl = self._bind_stream(c2) | flags
         with self._call_lock:
+            fl = self._bind_stream(c2) | flags
             self._check(self.lib.vw_energy(self.ctx, _vp(_ptr(c2)), c2.shape[0], c2.shape[1], _ld(c2),
                                            out.ctypes.data_as(_dp), fl))
         return float(out[0]) if one_d else out
@@ -474,8 +524,8 @@ class Engine:
         w = w_out if w_out is not None else torch.empty((nlevels, max(n_local, 1)), dtype=torch.float64,
                                                         device=vin_ext.device)
         v = v_out if v_out is not None else torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
-        fl = self._bind_stream(vin_ext, w, v) | flags
         with self._call_lock:
+            fl = self._bind_stream(vin_ext, w, v) | flags
             self._check(self.lib.vw_modwt_forward_span(
                 self.ctx, _vp(vin_ext.data_ptr()), int(halo), int(n_local), hs.ctypes.data_as(_dp),
                 gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), _vp(w.data_ptr()), w.stride(0),
@@ -488,8 +538,8 @@ class Engine:
         b, n = ext.shape[0], ext.shape[1] - hist
         hs, gs = _fp(hs), _fp(gs)
         assert ext.stride(1) == 1 and w_out.stride(1) == 1 and v_out.stride(1) == 1
-        fl = self._bind_stream(ext, w_out, v_out) | flags
         with self._call_lock:
+            fl = self._bind_stream(ext, w_out, v_out) | flags
             self._check(self.lib.vw_modwt_stream_level(
                 self.ctx, _vp(ext.data_ptr()), int(b), ext.stride(0), int(hist), int(n), hs.ctypes.data_as(_dp),
                 gs.ctypes.data_as(_dp), hs.size, int(level), _vp(w_out.data_ptr()), w_out.stride(0),
@@ -504,8 +554,8 @@ class Engine:
         if w_ext.stride(1) != 1:
             w_ext = w_ext.contiguous()
         out = out if out is not None else torch.empty(max(n_local, 1), dtype=torch.float64, device=vin_ext.device)
-        fl = self._bind_stream(vin_ext, w_ext, out) | flags
         with self._call_lock:
+            fl = self._bind_stream(vin_ext, w_ext, out) | flags
             self._check(self.lib.vw_modwt_inverse_span(
                 self.ctx, _vp(vin_ext.data_ptr()), _vp(w_ext.data_ptr()), w_ext.stride(0), int(halo), int(n_local),
                 hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), int(order),

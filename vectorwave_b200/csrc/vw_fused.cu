@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "vw_internal.cuh"
+#include "vw_tma.cuh"
 
 namespace {
 
@@ -39,105 +40,14 @@ namespace {
 #ifndef VW_WAVEFRONT
 #define VW_WAVEFRONT 0   // 1 (developer builds, untested on hardware): see the wavefront block in k_fused_analysis
 #endif
+#ifndef VW_EXP_NOSTORE
+#define VW_EXP_NOSTORE 0   // 1 (developer builds, WRONG results): the analysis tile kernel skips its global stores -- compute-only timing
+#endif
 #ifndef VW_STAGE_W
 #define VW_STAGE_W 1   // 0 (developer builds): detail rows of dilation 1 / 2 leave straight from registers instead of smem + bulk store
 #endif
 constexpr int kR = VW_KR;          // outputs per thread item (odd => conflict-free strided LDS.64)
 constexpr int kThreads = 256;  // maximum threads per CTA (launch bound); the launch may use fewer
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk async copies (TMA)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// global -> shared, completes on the mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// shared -> global, bulk async-group completion
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ------------------------------------------------------------------------------------------------
-// boundary extension of one position (used only for the few out-of-range halo samples)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t wrap_mod(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
-__device__ __forceinline__ double ext_load(const double *__restrict__ row, int64_t pos, int64_t n, int mode) {
-    if (pos >= 0 && pos < n) return __ldg(row + pos);
-    if (mode == VW_PERIODIC) return __ldg(row + wrap_mod(pos, n));
-    if (mode == VW_SYMMETRIC) { int64_t m = wrap_mod(pos, 2 * n); return __ldg(row + (m < n ? m : 2 * n - 1 - m)); }
-    return 0.0;  // zero padding / linear span
-}
-
-// Stage positions [pos0, pos0+count) of `row` (length n, boundary `mode`) into dst[0..count).
-// TMA path: contiguous in-range pieces as bulk copies on `bar` (thread 0), everything else by hand.
-// Returns nothing; caller waits on `bar` (when use_tma) and __syncthreads().
-__device__ __forceinline__ void stage_tile(double *dst, const double *__restrict__ row, int64_t pos0, int count, int64_t n,
-                                           int mode, bool use_tma, uint64_t *bar, bool row_is_null) {
-    const int tid = threadIdx.x;
-    if (row_is_null) {
-        for (int i = tid; i < count; i += (int)blockDim.x) dst[i] = 0.0;
-        if (use_tma && tid == 0) mbar_expect_tx(bar, 0);
-        return;
-    }
-    if (!use_tma) {
-        for (int i = tid; i < count; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
-        return;
-    }
-    if (mode == VW_PERIODIC) {
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)count * 8u);
-            int done = 0;
-            int64_t p = wrap_mod(pos0, n);
-            while (done < count) {
-                int64_t piece = n - p;
-                if (piece > count - done) piece = count - done;
-                bulk_g2s(dst + done, row + p, (uint32_t)piece * 8u, bar);
-                done += (int)piece;
-                p = 0;
-            }
-        }
-        return;
-    }
-    // non-periodic: one in-range piece [lo, hi), the rest (zeros or mirror) by hand
-    int64_t lo = pos0 < 0 ? 0 : pos0, hi = pos0 + count > n ? n : pos0 + count;
-    if (hi < lo) hi = lo;
-    int a = (int)(lo - pos0), b = (int)(hi - pos0);  // dst[a..b) in range
-    if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)(b - a) * 8u);
-        if (b > a) bulk_g2s(dst + a, row + lo, (uint32_t)(b - a) * 8u, bar);
-    }
-    for (int i = tid; i < a; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
-    for (int i = b + tid; i < count; i += (int)blockDim.x) dst[i] = ext_load(row, pos0 + i, n, mode);
-}
 
 // ------------------------------------------------------------------------------------------------
 // inner products
@@ -298,15 +208,6 @@ __device__ __forceinline__ void synthesis_item_dyn(const double *__restrict__ in
 // ------------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
-// L2 prefetch of [p, p + count) doubles clipped to the row [0, n): the future CTA's bulk copy then hits L2 instead of
-// queueing behind the stores in HBM (16-byte units; the rows are 16-byte aligned whenever the bulk path is on)
-__device__ __forceinline__ void prefetch_l2_span(const double *row, long long p, int count, long long n) {
-    long long lo = p < 0 ? 0 : p, hi = p + count > n ? n : p + count;
-    lo = (lo + 1) & ~1ll; hi &= ~1ll;
-    if (hi > lo)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row + lo), "r"((uint32_t)((hi - lo) * 8)) : "memory");
-}
-
 // Developer instrumentation (make EXTRA=-DVW_PHASE_CLOCKS): thread 0 of every analysis CTA stamps %globaltimer (ns) at its
 // phase boundaries -- [0] start, [1] input tile landed, [2 + lev] level done, [7] last bulk store read out -- plus the SM
 // id in [6]; tools/phase_clocks.py reads the log through vw_debug_phase_log and reports where a tile's lifetime goes.
@@ -491,6 +392,11 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
 
     double *cur = buf0, *nxt = buf1;
     int lo_prev = 0;
+#if VW_EXP_NOSTORE
+    const bool do_store = a.nlev > 64;   // never true; opaque to the compiler
+#else
+    constexpr bool do_store = true;
+#endif
     for (int lev = 0; lev < a.nlev; lev++) {
         const int ld2 = a.log2d0 + lev;
         const int d = 1 << ld2;
@@ -538,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
                 double *wq = (staged ? stg : wrow) + (base - HT);   // never dereferenced below r = rlo
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
-                    if (full || r < nvalid) { *q = ah[r]; if (r >= rlo) *wq = ag[r]; }
+                    if (full || r < nvalid) { *q = ah[r]; if (r >= rlo && (staged || do_store)) *wq = ag[r]; }
                     q += d; wq += d;
                 }
             }
@@ -623,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
             // a group has at most two staged levels (dilation 1 and 2) and each owns a staging buffer, so nothing is ever
             // written twice: no wait, no barrier -- the bulk store drains while the next level computes
             if (a.use_tma) {
-                if (tid == 0) {
+                if (tid == 0 && do_store) {
                     bulk_s2g(wrow, stg, (uint32_t)Tt * 8u);
                     bulk_commit();
                 }
@@ -638,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
     // V after the last level sits in cur[HT .. HT+Tt)
     double *vrow = a.v + b * a.ldv + (g0 - a.t0);
     if (a.use_tma) {
-        if (tid == 0) {
+        if (tid == 0 && do_store) {
             bulk_s2g(vrow, cur + HT, (uint32_t)Tt * 8u);
             bulk_commit();
             bulk_wait_read<0>();
@@ -811,20 +717,27 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
 // ------------------------------------------------------------------------------------------------
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// opt-in dynamic shared memory, raised once per kernel and size (the attribute is sticky; the call costs a microsecond)
+// opt-in dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is per function per DEVICE and absolute, and
+// several contexts may live on one device (one per host thread): the high-water mark is therefore process-global per
+// (device, function), under its own mutex, and only ever raised -- a ctx launching a smaller tile never lowers it
+// under another ctx's feet.
 template <typename K>
 int set_smem(vw_ctx *ctx, K kernel, size_t bytes) {
+    struct Entry { int device; const void *func; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Entry> marks;
     const void *func = (const void *)kernel;
-    for (auto &e : ctx->smem_set)
-        if (e.first == func) {
-            if (e.second >= bytes) return VW_OK;
-            e.second = bytes;
-            return vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                                 "cudaFuncSetAttribute(max dynamic smem)");
-        }
-    ctx->smem_set.push_back({func, bytes});
-    return vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                         "cudaFuncSetAttribute(max dynamic smem)");
+    std::lock_guard<std::mutex> lk(mu);
+    Entry *hit = nullptr;
+    for (auto &e : marks)
+        if (e.device == ctx->device && e.func == func) { hit = &e; break; }
+    if (hit && hit->bytes >= bytes) return VW_OK;
+    int rc = vw_cuda_check(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                           "cudaFuncSetAttribute(max dynamic smem)");
+    if (rc) return rc;
+    if (hit) hit->bytes = bytes;
+    else marks.push_back({ctx->device, func, bytes});
+    return VW_OK;
 }
 
 // from 16 taps on a quadrature-mirror pair (every orthogonal wavelet) takes the uniform-register QMF build
@@ -1030,6 +943,10 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     a.log2d0 = p.first_level - 1; a.mode = p.mode; a.tiles_per_row = (int)tiles_per_row;
     a.use_tma = use_tma; a.use_stage = use_stage; a.lrt = p.l;
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
+    if (use_tma && ctx->opt_lean) {   // the common case runs on the issue-lean kernels (vw_lean.cu)
+        const int rcl = vw_lean_forward(ctx, p, a.f, tile, htot, hexact, use_stage, launch_threads(ctx, p.l, true, p.nlevels));
+        if (rcl != VW_EUNSUPPORTED) return rcl;
+    }
 #if VW_WAVEFRONT
     {   // one item per thread at every level, dilation <= 32, bulk path, no per-level mirror patch
         bool ok = use_tma && p.mode != VW_SYMMETRIC && p.l <= VW_MERGED_MAXL && p.first_level + p.nlevels - 1 <= 6;
@@ -1104,6 +1021,10 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
     for (int k = 0; k < VW_FUSED_MAX_L; k++) {
         a.f.h[k] = k < p.l ? (rev_h ? f.h[p.l - 1 - k] : f.h[k]) : 0.0;
         a.f.g[k] = k < p.l ? (rev_g ? f.g[p.l - 1 - k] : f.g[k]) : 0.0;
+    }
+    if (use_tma && ctx->opt_lean && !aligned_stage) {
+        const int rcl = vw_lean_inverse(ctx, p, a.f, tile, htot, launch_threads(ctx, p.l, false, p.nlevels));
+        if (rcl != VW_EUNSUPPORTED) return rcl;
     }
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -63,9 +64,23 @@ struct vw_ctx {
     size_t pinned_bytes = 0;
     struct PlanEntry { bool forward; int l, levels; int64_t n; std::vector<VwPlanGroup> groups; };
     mutable std::vector<PlanEntry> plan_cache;   // launch plans by shape (the planner costs 2-35 us); cleared by vw_set_option
-    std::vector<std::pair<const void *, size_t>> smem_set;   // dynamic shared memory already opted in, per kernel
+    // Scratch is per ctx, not per stream: a call that returned without synchronising (VW_FLAG_NO_SYNC) leaves an event
+    // behind, and the next call that takes scratch on a DIFFERENT stream waits on it first (vw_scratch)
+    bool capturing = false;   // between vw_graph_begin and vw_graph_end: calls are recorded, nothing may synchronise
+    int call_depth = 0;       // public entry points nest (handle / *_all calls use the plain ones)
+    int64_t opt_timing = 0;
+    cudaEvent_t time_ev[2] = {nullptr, nullptr};
+    int64_t time_launch0 = 0;
+    std::chrono::steady_clock::time_point time_host0;
+    float time_host_ms = 0.f;
+    int32_t time_launches = 0;
+    bool time_valid = false;
+    cudaEvent_t scratch_event = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_pending = false;
     struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
     std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
+    int64_t opt_lean = 1;    // issue-lean tile kernels (vw_lean.cu): bit 0 = filters up to 12 taps, bit 1 = 16..20-tap quadrature-mirror pairs
     int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
     std::recursive_mutex mu;   // every public entry point holds it: calls on one ctx from several host threads serialise
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
@@ -92,6 +107,35 @@ __device__ __forceinline__ double vw_threshold_nonneg(double c, double lam, int 
 #endif
 
 int vw_fail(vw_ctx *ctx, int status, const char *fmt, ...);
+
+// helpers of vw_shim.cu that the other host-side translation units (vw_multi.cu) use
+namespace vwshim {
+struct DeviceGuard {
+    std::unique_lock<std::recursive_mutex> lk;
+    vw_ctx *ctx = nullptr;
+    int prev = -1;
+    bool ranged = false, timed = false;
+    explicit DeviceGuard(int dev);
+    DeviceGuard(vw_ctx *ctx, const char *name);
+    ~DeviceGuard();
+    void enter(int dev);
+};
+int load_filters(vw_ctx *ctx, const double *hs, const double *gs, int l, VwFilt &f);
+int check_mode(vw_ctx *ctx, int mode);
+int check_levels(vw_ctx *ctx, int64_t n, int l, int levels);
+int check_signal_args(vw_ctx *ctx, const void *x, int64_t batch, int64_t n, int64_t ld);
+int check_finite(vw_ctx *ctx, const double *x_dev, int64_t batch, int64_t n, int64_t ld, const char *what);
+int no_capture(vw_ctx *ctx, const char *what);
+int pinned_mailbox(vw_ctx *ctx, size_t bytes, void **out);
+int copy_rows(vw_ctx *ctx, void *dst, int64_t ld_dst, const void *src, int64_t ld_src, int64_t n, int64_t rows, cudaMemcpyKind kind);
+int finish(vw_ctx *ctx, uint32_t flags, bool host_io);
+int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64_t ldx, const VwFilt &f, int l, int levels,
+                   int mode, double *w, int64_t ldw, int64_t lsw, double *vj, int64_t ldv, uint32_t flags);
+int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const double *vj, int64_t ldv, int64_t batch,
+                   int64_t n, const VwFilt &f, int l, int levels, int mode, const vw_align *align, int order,
+                   uint64_t detail_mask, int use_approx, double *xout, int64_t ldx, uint32_t flags, const double *thr_dev,
+                   int thr_per_row, int thr_soft);
+}  // namespace vwshim
 int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what);
 int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out);
 
@@ -141,6 +185,12 @@ struct VwFusedInv {
 #include <vector>
 int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out);
 int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f);
+
+// ---- issue-lean tile kernels of the common case (vw_lean.cu); geometry chosen by vw_fused_forward / vw_fused_inverse ----
+#define VW_LEAN_MAX_L 20
+int vw_lean_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt32 &f, int64_t tile, int64_t htot, int64_t hexact,
+                    bool use_stage, int nthreads);
+int vw_lean_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt32 &f, int64_t tile, int64_t htot, int nthreads);
 
 // first level (1-based) the column kernels take for filter length l: dilation >= 32 normally; FP64-bound filters
 // (l >= 24) already from dilation 4 (analysis) / 16 (synthesis, whose two input streams suffer more from 32-byte row pieces)

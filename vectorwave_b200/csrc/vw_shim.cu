@@ -8,6 +8,10 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
+#include <chrono>
+
 #include "vw_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -34,6 +38,15 @@ int vw_cuda_check(vw_ctx *ctx, cudaError_t e, const char *what) {
 int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     slot += ctx->scratch_set * vw_ctx::kScratch;
+    if (ctx->capturing && ctx->scratch_bytes[slot] < bytes)
+        return vw_fail(ctx, VW_ESTATE, "scratch buffer %d would have to grow during graph capture: run the same calls once "
+                                       "before vw_graph_begin", slot);
+    if (ctx->scratch_pending && ctx->scratch_stream != ctx->stream && !ctx->capturing) {
+        // the previous un-synchronised call may still be using the scratch on its own stream: order this stream after it
+        int rc = vw_cuda_check(ctx, cudaStreamWaitEvent(ctx->stream, ctx->scratch_event, 0), "scratch hand-over between streams");
+        if (rc) return rc;
+        ctx->scratch_stream = ctx->stream;   // this stream now runs after it; later calls on it need no second wait
+    }
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
             cudaStreamSynchronize(ctx->stream);
@@ -50,23 +63,45 @@ int vw_scratch(vw_ctx *ctx, int slot, size_t bytes, void **out) {
     return VW_OK;
 }
 
-namespace {
+namespace vwshim {
 
-// Held for the duration of a public call: the ctx's mutex (scratch buffers, stream binding, error string and launch
-// counter are per ctx, so concurrent callers of one ctx serialise -- the reference's transforms are shared across
-// threads) and the ctx's device as the current one.
-struct DeviceGuard {
-    std::unique_lock<std::recursive_mutex> lk;
-    int prev = -1;
-    explicit DeviceGuard(int dev) { enter(dev); }
-    explicit DeviceGuard(vw_ctx *ctx) : lk(ctx->mu) { enter(ctx->device); }
-    void enter(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
+// DeviceGuard (vw_internal.cuh) is held for the duration of a public call: the ctx's mutex (scratch buffers, stream
+// binding, error string and launch counter are per ctx, so concurrent callers of one ctx serialise -- the reference's
+// transforms are shared across threads), the ctx's device as the current one, an NVTX range named after the entry
+// point, and -- with vw_set_option("timing", 1) -- a CUDA event pair around the call's device work.
+void DeviceGuard::enter(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+}
+DeviceGuard::DeviceGuard(int dev) { enter(dev); }
+DeviceGuard::DeviceGuard(vw_ctx *c, const char *name) : lk(c->mu), ctx(c) {
+    enter(c->device);
+    if (++c->call_depth > 1) return;          // nested public calls (the *_all and handle entry points) report as one
+    if (name) { nvtxRangePushA(name); ranged = true; }
+    if (c->opt_timing && !c->capturing) {
+        if (!c->time_ev[0]) {
+            cudaEventCreate(&c->time_ev[0]);
+            cudaEventCreate(&c->time_ev[1]);
+        }
+        cudaEventRecord(c->time_ev[0], c->stream);
+        c->time_launch0 = c->launches;
+        c->time_host0 = std::chrono::steady_clock::now();
+        timed = true;
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
+}
+DeviceGuard::~DeviceGuard() {
+    if (ctx && --ctx->call_depth == 0) {
+        if (timed) {
+            cudaEventRecord(ctx->time_ev[1], ctx->stream);
+            ctx->time_host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->time_host0).count();
+            ctx->time_launches = (int32_t)(ctx->launches - ctx->time_launch0);
+            ctx->time_valid = true;
+        }
+        if (ranged) nvtxRangePop();
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+}
 
 int pinned_mailbox(vw_ctx *ctx, size_t bytes, void **out) {
     if (ctx->pinned_bytes < bytes) {
@@ -112,7 +147,14 @@ int check_levels(vw_ctx *ctx, int64_t n, int l, int levels) {
     return VW_OK;
 }
 
+// entry points that need an answer from the device (or a host-side wait) cannot be captured into a graph
+int no_capture(vw_ctx *ctx, const char *what) {
+    if (ctx->capturing) return vw_fail(ctx, VW_ESTATE, "%s needs a device-to-host answer and cannot be captured into a graph", what);
+    return VW_OK;
+}
+
 int check_finite(vw_ctx *ctx, const double *x_dev, int64_t batch, int64_t n, int64_t ld, const char *what) {
+    if (int rc0 = no_capture(ctx, "VW_FLAG_CHECK_FINITE")) return rc0;
     void *cnt = nullptr, *mb = nullptr;
     int rc = vw_scratch(ctx, 5, 64, &cnt);
     if (rc) return rc;
@@ -137,7 +179,21 @@ int copy_rows(vw_ctx *ctx, void *dst, int64_t ld_dst, const void *src, int64_t l
 }
 
 int finish(vw_ctx *ctx, uint32_t flags, bool host_io) {
-    if (host_io || !(flags & VW_FLAG_NO_SYNC)) return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+    if (ctx->capturing) return VW_OK;   // nothing runs now; the graph launch decides about synchronising
+    if (host_io || !(flags & VW_FLAG_NO_SYNC)) {
+        int rc = vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+        if (ctx->scratch_stream == ctx->stream) ctx->scratch_pending = false;   // the stream the scratch was last used on has drained
+        return rc;
+    }
+    // returning with work in flight: mark where the scratch buffers become free again
+    if (!ctx->scratch_event) {
+        int rc = vw_cuda_check(ctx, cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming), "scratch event");
+        if (rc) return rc;
+    }
+    int rc = vw_cuda_check(ctx, cudaEventRecord(ctx->scratch_event, ctx->stream), "scratch event record");
+    if (rc) return rc;
+    ctx->scratch_pending = true;
+    ctx->scratch_stream = ctx->stream;
     return VW_OK;
 }
 
@@ -299,7 +355,12 @@ struct PipeGuard {
     vw_ctx *ctx;
     cudaStream_t saved;
     explicit PipeGuard(vw_ctx *c) : ctx(c), saved(c->stream) {}
-    ~PipeGuard() { ctx->stream = saved; ctx->scratch_set = 0; }
+    // every exit path, errors included: chunks already enqueued may still be copying into the caller's buffers and
+    // using both scratch sets, so nothing is handed back before both pipeline streams have drained
+    ~PipeGuard() {
+        for (int i = 0; i < 2; i++) if (ctx->pipe_stream[i]) cudaStreamSynchronize(ctx->pipe_stream[i]);
+        ctx->stream = saved; ctx->scratch_set = 0;
+    }
 };
 
 int pipe_streams(vw_ctx *ctx) {
@@ -314,7 +375,7 @@ int pipe_streams(vw_ctx *ctx) {
 // rows per chunk: chunks of >= 16 MB staged bytes, at most 8 of them, at least 2
 int64_t pipe_rows(const vw_ctx *ctx, int64_t batch, int64_t n, int levels) {
     const double total = (double)batch * (double)n * 8.0 * (levels + 2);
-    if (ctx->opt_pipe_min <= 0 || batch < 2 || total < (double)ctx->opt_pipe_min) return 0;
+    if (ctx->opt_pipe_min <= 0 || batch < 2 || total < (double)ctx->opt_pipe_min || ctx->capturing) return 0;
     int64_t chunks = (int64_t)(total / (16.0 * 1048576.0));
     chunks = std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(chunks, 8), batch));
     return (batch + chunks - 1) / chunks;
@@ -389,7 +450,8 @@ int check_signal_args(vw_ctx *ctx, const void *x, int64_t batch, int64_t n, int6
     return VW_OK;
 }
 
-}  // namespace
+}  // namespace vwshim
+using namespace vwshim;
 
 // ------------------------------------------------------------------------------------------------
 // extern "C"
@@ -440,12 +502,16 @@ int vw_init(int device, vw_ctx **out) {
 
 int vw_destroy(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 2 * vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
-    for (int i = 0; i < 2; i++) if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    {
+        DeviceGuard g(ctx, "vw_destroy");   // released before the ctx (and its mutex) goes away
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2 * vw_ctx::kScratch; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+        for (int i = 0; i < 2; i++) if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+        for (int i = 0; i < 2; i++) if (ctx->time_ev[i]) cudaEventDestroy(ctx->time_ev[i]);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    }
     delete ctx;
     return VW_OK;
 }
@@ -468,7 +534,8 @@ int vw_reset_stream(vw_ctx *ctx) {
 
 int vw_synchronize(vw_ctx *ctx) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_synchronize");
+    if (int rc0 = no_capture(ctx, "vw_synchronize")) return rc0;
     return vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
 }
 
@@ -484,7 +551,9 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
     else if (!strcmp(name, "wave")) ctx->opt_wave = value;
     else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
+    else if (!strcmp(name, "lean")) ctx->opt_lean = value;
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
+    else if (!strcmp(name, "timing")) ctx->opt_timing = value;       // event pair around every public call (vw_last_timing)
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);
     ctx->plan_cache.clear();   // plans depend on the knobs
     return VW_OK;
@@ -536,24 +605,27 @@ void vw_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 int vw_device_alloc(vw_ctx *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_device_alloc");
     return vw_cuda_check(ctx, cudaMalloc(out, bytes ? bytes : 16), "vw_device_alloc");
 }
 int vw_device_free(vw_ctx *ctx, void *p) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_device_free");
+    if (int rc0 = no_capture(ctx, "vw_device_free")) return rc0;
     cudaStreamSynchronize(ctx->stream);
     return vw_cuda_check(ctx, cudaFree(p), "vw_device_free");
 }
 int vw_copy_h2d(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx || !dst || !src) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_copy_h2d");
+    if (int rc0 = no_capture(ctx, "vw_copy_h2d")) return rc0;
     int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "h2d");
     return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "h2d sync");
 }
 int vw_copy_d2h(vw_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx || !dst || !src) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_copy_d2h");
+    if (int rc0 = no_capture(ctx, "vw_copy_d2h")) return rc0;
     int rc = vw_cuda_check(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "d2h");
     return rc ? rc : vw_cuda_check(ctx, cudaStreamSynchronize(ctx->stream), "d2h sync");
 }
@@ -578,7 +650,7 @@ int64_t vw_span_halo(int32_t l, int32_t first_level, int32_t nlevels) {
 int vw_conv_modwt(vw_ctx *ctx, const double *x, int64_t n, const double *filter, int64_t lf, int32_t mode, double *out,
                   uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_conv_modwt");
     if (!x || !filter || !out) return vw_fail(ctx, VW_ENULL, "signal, filter and output cannot be null");
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
@@ -605,7 +677,7 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
                      const double *gs, int32_t l, int32_t levels, int32_t mode, double *w, int64_t ldw,
                      int64_t level_stride_w, double *vj, int64_t ldv, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_forward");
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
@@ -644,7 +716,7 @@ int vw_modwt_forward(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int
 int vw_modwt_forward_soa(vw_ctx *ctx, const double *soa_x, int64_t batch, int64_t n, const double *hs, const double *gs,
                          int32_t l, int32_t levels, double *const *soa_w, double *soa_v, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_forward_soa");
     int rc;
     if ((rc = check_signal_args(ctx, soa_x, batch, n, n))) return rc;
     if (!soa_w || !soa_v) return vw_fail(ctx, VW_ENULL, "output buffers cannot be null");
@@ -705,7 +777,7 @@ int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_st
                      int32_t mode, const vw_align *align, int32_t order, uint64_t detail_mask, int32_t use_approx,
                      double *xout, int64_t ldx, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_inverse");
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if (!w || !vj) return vw_fail(ctx, VW_ENULL, "coefficient buffers cannot be null");
@@ -756,7 +828,8 @@ int vw_modwt_inverse(vw_ctx *ctx, const double *w, int64_t ldw, int64_t level_st
 int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t ld, const double *thresholds,
                  int32_t per_row, int32_t soft, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_threshold");
+    if (int rc0 = no_capture(ctx, "vw_threshold (host thresholds)")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, coeffs, batch, n, ld))) return rc;
     if (!thresholds) return vw_fail(ctx, VW_ENULL, "thresholds cannot be null");
@@ -782,7 +855,8 @@ int vw_threshold(vw_ctx *ctx, double *coeffs, int64_t batch, int64_t n, int64_t 
 int vw_universal_threshold(vw_ctx *ctx, const double *w1, int64_t batch, int64_t n, int64_t ld, double *thresholds_out,
                            uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_universal_threshold");
+    if (int rc0 = no_capture(ctx, "vw_universal_threshold")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, w1, batch, n, ld))) return rc;
     if (!thresholds_out) return vw_fail(ctx, VW_ENULL, "thresholds_out cannot be null");
@@ -808,7 +882,8 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
                    const double *gs, int32_t l, int32_t levels, int32_t mode, const vw_align *align, int32_t order,
                    double threshold, int32_t soft, double *out, int64_t ldo, double *thresholds_out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_swt_denoise");
+    if (int rc0 = no_capture(ctx, "vw_swt_denoise")) return rc0;
     int rc;
     if ((rc = check_mode(ctx, mode))) return rc;
     if ((rc = check_signal_args(ctx, x, batch, n, ldx))) return rc;
@@ -862,7 +937,8 @@ int vw_swt_denoise(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
 
 int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_median_abs");
+    if (int rc0 = no_capture(ctx, "vw_median_abs")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -885,7 +961,8 @@ int vw_median_abs(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_
 int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *mean_out, double *var_out,
                      uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_mean_variance");
+    if (int rc0 = no_capture(ctx, "vw_mean_variance")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!mean_out || !var_out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -909,7 +986,8 @@ int vw_mean_variance(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int
 int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, const double *sigma,
                       double *thr_out, double *risk_out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_sure_threshold");
+    if (int rc0 = no_capture(ctx, "vw_sure_threshold")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!sigma || !thr_out) return vw_fail(ctx, VW_ENULL, "sigma and thr_out cannot be null");
@@ -944,7 +1022,8 @@ int vw_sure_threshold(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, in
 
 int vw_energy(vw_ctx *ctx, const double *c, int64_t batch, int64_t n, int64_t ld, double *out, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_energy");
+    if (int rc0 = no_capture(ctx, "vw_energy")) return rc0;
     int rc;
     if ((rc = check_signal_args(ctx, c, batch, n, ld))) return rc;
     if (!out) return vw_fail(ctx, VW_ENULL, "out cannot be null");
@@ -969,7 +1048,7 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
                           const double *gs, int32_t l, int32_t first_level, int32_t nlevels, double *w,
                           int64_t level_stride_w, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_forward_span");
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
@@ -1039,7 +1118,7 @@ int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t
                           const double *hs, const double *gs, int32_t l, int32_t level, double *w, int64_t ldw,
                           double *v, int64_t ldv, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_stream_level");
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "streaming calls take device pointers only");
     if (!vin || !w || !v) return vw_fail(ctx, VW_ENULL, "stream buffers cannot be null");
@@ -1077,7 +1156,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                           int64_t n_local, const double *hs, const double *gs, int32_t l, int32_t first_level,
                           int32_t nlevels, int32_t order, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
-    DeviceGuard g(ctx);
+    DeviceGuard g(ctx, "vw_modwt_inverse_span");
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");

@@ -166,13 +166,15 @@ class _StreamingBase:
         buf = np.concatenate([self._tail, data]) if self._tail.size else data
         bs, hop = self.bufferSize, self._hop
         nw = 0 if buf.size < bs else (buf.size - bs) // hop + 1
+        # The reference has already stored the samples in its ring when a window fails (non-finite values, level
+        # errors): commit the tail -- with the attempted windows consumed -- whether or not _run raises
+        self._tail = buf[nw * hop:].copy()
+        self._stats._add_samples(int(data.size))
         if nw:
             t0 = time.perf_counter_ns()
             windows = np.lib.stride_tricks.as_strided(buf, shape=(nw, bs), strides=(hop * 8, 8), writeable=False)
             self._run(np.ascontiguousarray(windows))
             self._stats._record_blocks(nw, time.perf_counter_ns() - t0)
-        self._tail = buf[nw * hop:].copy()
-        self._stats._add_samples(int(data.size))
 
     def _flush_window(self):
         final = np.zeros((1, self.bufferSize))
