@@ -376,6 +376,10 @@ VW_API int vw_graph_destroy(vw_ctx *ctx, vw_graph *g);
  * launched.  Also wraps each call in an NVTX range ("vw_modwt_forward", ...) visible to Nsight tools. */
 typedef struct vw_timing { float device_ms; float host_ms; int32_t launches; int32_t reserved; } vw_timing;
 VW_API int vw_last_timing(vw_ctx *ctx, vw_timing *out);
+/* The FP64 roofline denominator measured on this device: sustained TFLOP/s of the DFMA stream the tile kernels are made
+ * of (one uniform-register operand, 8 independent chains, 64 warps per SM, a few milliseconds).  MEASURED_PEAKS.json has
+ * no FP64 figure; bench.py calls this once per run.  sm_mhz_out (may be NULL): the device's maximum SM clock. */
+VW_API int vw_probe_fp64(vw_ctx *ctx, double *tflops_out, double *sm_mhz_out);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,64 @@ class NumpySpanEngine:
         return out
 
 
+    # -- the whole-cascade calls of the default path, restated from the contract in include/vw_modwt.h (vw_span_plan,
+    #    vw_modwt_forward_span_all, vw_span_pack_inverse / unpack, vw_modwt_inverse_span_all) on top of the calls above
+    def forward_span_all(self, xext, plan, hs, gs, w, v, flags=0):
+        n, lead, lead_w = int(plan.n_local), int(plan.lead), int(plan.lead_w)
+        ng = plan.ngroups_f
+        rf = [sum(plan.halo_f[g + 1:ng]) for g in range(ng)]
+        cur, have = xext, lead                                   # cur[0] is position -have
+        for g in range(ng):
+            keep, first, nlev = rf[g], plan.first_f[g], plan.nlev_f[g]
+            vout = v if g + 1 == ng else torch.empty(keep + n, dtype=torch.float64)
+            self.forward_span(cur, have - keep, hs, gs, first, nlev, w_out=w[first - 1:first - 1 + nlev, lead_w - keep:],
+                              v_out=vout)
+            cur, have = vout, keep
+
+    @staticmethod
+    def _msg_layout(plan):
+        ng = plan.ngroups_i
+        si_in, acc = [], 0
+        for g in range(ng):
+            acc += plan.halo_i[g]
+            si_in.append(acc)
+        pieces = [(None, si_in[ng - 1])]                         # (row or None for V_J, count)
+        for g in range(ng):
+            pieces += [(plan.first_i[g] - 1 + i, si_in[g]) for i in range(plan.nlev_i[g])]
+        return si_in, pieces
+
+    def span_pack_inverse(self, plan, w, v, msg):
+        _, pieces = self._msg_layout(plan)
+        at, lw = 0, int(plan.lead_w)
+        for row, cnt in pieces:
+            msg[at:at + cnt] = v[:cnt] if row is None else w[row, lw:lw + cnt]
+            at += cnt
+        assert at == int(plan.inverse_msg)
+
+    def span_unpack_inverse(self, plan, msg, w, v):
+        _, pieces = self._msg_layout(plan)
+        at, lw, n = 0, int(plan.lead_w), int(plan.n_local)
+        for row, cnt in pieces:
+            src = msg[at:at + cnt] if msg is not None else torch.zeros(cnt, dtype=torch.float64)
+            if row is None:
+                v[n:n + cnt] = src
+            else:
+                w[row, lw + n:lw + n + cnt] = src
+            at += cnt
+
+    def inverse_span_all(self, plan, w, v, hs, gs, order, out, flags=0):
+        si_in, _ = self._msg_layout(plan)
+        n, lw, ng = int(plan.n_local), int(plan.lead_w), plan.ngroups_i
+        vext = v
+        for g in range(ng - 1, -1, -1):
+            s_in, s_out = si_in[g], si_in[g] - plan.halo_i[g]
+            first, nlev = plan.first_i[g], plan.nlev_i[g]
+            dst = out if g == 0 else torch.empty(n + s_out, dtype=torch.float64)
+            self.inverse_span(vext[:n + s_in], w[first - 1:first - 1 + nlev, lw:lw + n + s_in], s_in - s_out, hs, gs, first, nlev,
+                              order, out=dst)
+            vext = dst
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

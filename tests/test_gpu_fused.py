@@ -15,7 +15,7 @@ REL = 1e-12
 
 
 def tol(x):
-    return REL * max(1.0, float(np.max(np.abs(x))))
+    return REL * float(np.max(np.abs(x)))      # north_star: every coefficient within 1e-12 * max|x| per level
 
 
 @pytest.fixture()
@@ -386,6 +386,43 @@ def test_baseline_full_sizes(eng, name, b, n, levels, rt_tol):
             approx_only = eng.inverse(wm, vm, hs, gs, mode, align, order, detail_mask=0)
             assert float((den2 - approx_only).abs().max()) <= 1e-12 * scale    # every detail removed
             del ref, den, den2, approx_only
+
+
+@pytest.mark.parametrize("name,b,n,levels,modes", [
+    ("sym8", 1024, 65536, 8, (0,)),          # config #3: all 8 levels
+    ("coif5", 1, 1 << 24, 10, (0,)),         # config #4's plan (tile kernels for levels 1-2, column kernels 3-10) at 2^24
+    ("db8", 256, 1 << 20, 6, (0, 1, 2)),     # config #5: all three boundary modes, forward + inverse + denoise
+])
+def test_baseline_full_sizes_one_row_against_the_oracle(eng, name, b, n, levels, modes):
+    """The full-size configs run tiles / plans no small case reaches, so one row of each is compared with the oracle at
+    FULL length: every level of the decomposition, the reconstruction, and (config #5) the SWT denoise, per mode.  The row
+    is the LAST one of the batch (the last CTAs of the grid); the oracle uses its sparse a-trous loops (same sums as the
+    reference's dense upsampled filters, minus the multiplications by zero)."""
+    import torch
+    from vectorwave_b200.modwt import multilevel_alignment
+    h, g, wid = filters(name)
+    hs, gs = h * S, g * S
+    x = _device_signal(b, n, 99)
+    row = x[b - 1].cpu().numpy()
+    t = REL * float(np.max(np.abs(row)))
+    bms = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC]
+    for mode in modes:
+        align, order = multilevel_alignment(vw.get_wavelet(name), bms[mode], levels)
+        w, v = eng.forward(x, hs, gs, levels, mode)
+        xr = eng.inverse(w, v, hs, gs, mode, align, order)
+        wo, vo = cref.decompose(row, h, g, levels, mode)
+        for j in range(levels):
+            assert float(np.max(np.abs(w[j, b - 1].cpu().numpy() - wo[j]))) <= t, f"W_{j + 1}, mode {mode}"
+        assert float(np.max(np.abs(v[b - 1].cpu().numpy() - vo))) <= t
+        ref = cref.reconstruct(wo, vo, h, g, mode, wid)
+        assert float(np.max(np.abs(xr[b - 1].cpu().numpy() - ref))) <= REL * max(float(np.max(np.abs(ref))), float(np.max(np.abs(row))))
+        del w, v, xr
+        if name == "db8":
+            den, thr = eng.denoise(x, hs, gs, levels, mode, align, order, -1.0, True)
+            dref, tref = cref.swt_denoise(row, h, g, levels, mode, wid, -1.0, True)
+            assert abs(float(thr[b - 1]) - tref) <= 1e-12 * tref
+            assert float(np.max(np.abs(den[b - 1].cpu().numpy() - dref))) <= t
+            del den
 
 
 def test_seeded_random_shapes_against_the_oracle(eng):

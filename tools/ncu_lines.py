@@ -50,7 +50,7 @@ for i, r in enumerate(body):
         if v:
             per[key][2][n[6:]] += v
     tot += s
-src = open("vectorwave_b200/csrc/vw_fused.cu").read().split("\n")
+src = open("" + (sys.argv[6] if len(sys.argv) > 6 else "vectorwave_b200/csrc/vw_fused.cu") + "").read().split("\n")
 print(f"total samples {tot}")
 for (line, ctx), (s, ex, c) in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
     text = src[line - 1].strip()[:70] if 0 < line <= len(src) else "?"

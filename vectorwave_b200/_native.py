@@ -136,6 +136,7 @@ SIGNATURES = {
     "vw_graph_launch": (C.c_int, [_vp, _vp, _u32]),
     "vw_graph_destroy": (C.c_int, [_vp, _vp]),
     "vw_last_timing": (C.c_int, [_vp, C.POINTER(VwTiming)]),
+    "vw_probe_fp64": (C.c_int, [_vp, _dp, _dp]),
 }
 
 _lib = None
@@ -561,3 +562,232 @@ class Engine:
                 hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), hs.size, int(first_level), int(nlevels), int(order),
                 _vp(out.data_ptr()), fl))
         return out
+
+    # -- span-sharded cascades, up-front halo schedule (one ABI call per direction) ------------------------
+    def forward_span_all(self, xext, plan, hs, gs, w, v, flags=0):
+        """xext [lead | n_local] (halo in place), w [levels][row_stride], v [n_local + pad]: CUDA tensors."""
+        hs, gs = _fp(hs), _fp(gs)
+        with self._call_lock:
+            fl = self._bind_stream(xext, w, v) | flags
+            self._check(self.lib.vw_modwt_forward_span_all(self.ctx, _vp(xext.data_ptr()), C.byref(plan), hs.ctypes.data_as(_dp),
+                                                           gs.ctypes.data_as(_dp), _vp(w.data_ptr()), w.stride(0),
+                                                           _vp(v.data_ptr()), fl))
+
+    def span_pack_inverse(self, plan, w, v, msg):
+        with self._call_lock:
+            fl = self._bind_stream(w, v, msg)
+            self._check(self.lib.vw_span_pack_inverse(self.ctx, C.byref(plan), _vp(w.data_ptr()), w.stride(0),
+                                                      _vp(v.data_ptr()), _vp(msg.data_ptr()), fl))
+
+    def span_unpack_inverse(self, plan, msg, w, v):
+        """msg None: the open end of a ZERO_PADDING signal (zeros)."""
+        with self._call_lock:
+            fl = self._bind_stream(w, v, msg)
+            self._check(self.lib.vw_span_unpack_inverse(self.ctx, C.byref(plan), _vp(msg.data_ptr() if msg is not None else None),
+                                                        _vp(w.data_ptr()), w.stride(0), _vp(v.data_ptr()), fl))
+
+    def inverse_span_all(self, plan, w, v, hs, gs, order, out, flags=0):
+        hs, gs = _fp(hs), _fp(gs)
+        with self._call_lock:
+            fl = self._bind_stream(w, v, out) | flags
+            self._check(self.lib.vw_modwt_inverse_span_all(self.ctx, C.byref(plan), _vp(w.data_ptr()), w.stride(0),
+                                                           _vp(v.data_ptr()), hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp),
+                                                           int(order), _vp(out.data_ptr()), fl))
+
+    # -- timing record / graph replay ----------------------------------------------------------------------
+    def last_timing(self):
+        """(device_ms, host_ms, launches) of the last public call; needs set_option("timing", 1)."""
+        t = VwTiming()
+        self._check(self.lib.vw_last_timing(self.ctx, C.byref(t)))
+        return float(t.device_ms), float(t.host_ms), int(t.launches)
+
+    def probe_fp64(self):
+        """(sustained FP64 FMA TFLOP/s measured now on this device, max SM MHz)"""
+        t, m = C.c_double(0.0), C.c_double(0.0)
+        with self._call_lock:
+            self._check(self.lib.vw_reset_stream(self.ctx))
+            self._check(self.lib.vw_probe_fp64(self.ctx, C.byref(t), C.byref(m)))
+        return float(t.value), float(m.value)
+
+    def capture(self):
+        """`with eng.capture() as g: eng.forward(...)` records the calls into one CUDA graph; `g.launch()` replays them."""
+        return _GraphCapture(self)
+
+    # -- device-resident results -------------------------------------------------------------------------------
+    def decompose_resident(self, x, hs, gs, levels, mode, result=None, flags=0):
+        """vw_modwt_decompose_h: the coefficients stay in HBM behind a DeviceResult (reused when `result` has the shape)."""
+        x2, _ = self._rows(x)
+        b, n = x2.shape
+        hs, gs = _fp(hs), _fp(gs)
+        res = result if result is not None else DeviceResult(self)
+        with self._call_lock:
+            fl = self._bind_stream(x2) | flags
+            self._check(self.lib.vw_modwt_decompose_h(self.ctx, _vp(_ptr(x2)), b, n, _ld(x2), hs.ctypes.data_as(_dp),
+                                                      gs.ctypes.data_as(_dp), hs.size, int(levels), int(mode),
+                                                      C.byref(res.handle), fl))
+        return res
+
+
+def span_plan(l, levels, n_local, world):
+    """vw_span_plan_query: layout + launch groups of the up-front span schedule (host logic only)."""
+    plan = VwSpanPlan()
+    rc = load_library().vw_span_plan_query(int(l), int(levels), int(n_local), int(world), C.byref(plan))
+    if rc == 7:
+        raise IllegalArgumentException("the total halo exceeds the per-rank span: use fewer ranks or levels")
+    if rc == 5:
+        raise InvalidArgumentException("upsampled filter longer than the signal", ErrorCode.VAL_TOO_LARGE)
+    if rc != VW_OK:
+        raise IllegalArgumentException(f"vw_span_plan_query failed: {rc}")
+    return plan
+
+
+class _GraphCapture:
+    def __init__(self, eng):
+        self.eng, self.handle = eng, _vp()
+
+    def __enter__(self):
+        with self.eng._call_lock:
+            self.eng._check(self.eng.lib.vw_reset_stream(self.eng.ctx))
+            self.eng._check(self.eng.lib.vw_graph_begin(self.eng.ctx))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        rc = self.eng.lib.vw_graph_end(self.eng.ctx, C.byref(self.handle))
+        if et is None:
+            self.eng._check(rc)
+        return False
+
+    def launch(self, flags=0):
+        with self.eng._call_lock:
+            self.eng._check(self.eng.lib.vw_reset_stream(self.eng.ctx))
+            self.eng._check(self.eng.lib.vw_graph_launch(self.eng.ctx, self.handle, flags))
+
+    def close(self):
+        if self.handle:
+            self.eng.lib.vw_graph_destroy(self.eng.ctx, self.handle)
+            self.handle = _vp()
+
+
+class DeviceResult:
+    """A MultiLevelMODWTResult whose coefficients live in HBM (vw_result): levels come to the host only on request."""
+
+    def __init__(self, eng):
+        self.eng, self.handle = eng, _vp()
+
+    def shape(self):
+        b, n, j = _i64(), _i64(), _i32()
+        self.eng._check(self.eng.lib.vw_result_shape(self.handle, C.byref(b), C.byref(n), C.byref(j)))
+        return int(b.value), int(n.value), int(j.value)
+
+    def get_level(self, level, out=None):
+        """level 1..J: detail coefficients; 0: approximation -> [B][N] host array (or into a CUDA tensor `out`)."""
+        b, n, _ = self.shape()
+        res = out if out is not None else np.empty((b, n))
+        with self.eng._call_lock:
+            fl = self.eng._bind_stream(res)
+            self.eng._check(self.eng.lib.vw_result_get_level(self.eng.ctx, self.handle, int(level), _vp(_ptr(res)), _ld(res), fl))
+        return res
+
+    def set_level(self, level, src):
+        s2, _ = self.eng._rows(src, "coefficients")
+        with self.eng._call_lock:
+            fl = self.eng._bind_stream(s2)
+            self.eng._check(self.eng.lib.vw_result_set_level(self.eng.ctx, self.handle, int(level), _vp(_ptr(s2)), _ld(s2), fl))
+
+    def threshold(self, level, thresholds, soft):
+        thr = np.atleast_1d(np.asarray(thresholds, dtype=np.float64))
+        with self.eng._call_lock:
+            self.eng._bind_stream()
+            self.eng._check(self.eng.lib.vw_result_threshold(self.eng.ctx, self.handle, int(level), thr.ctypes.data_as(_dp),
+                                                             int(thr.size > 1), int(bool(soft))))
+
+    def universal_threshold(self, soft=True):
+        b = self.shape()[0]
+        thr = np.empty(b)
+        with self.eng._call_lock:
+            self.eng._bind_stream()
+            self.eng._check(self.eng.lib.vw_result_universal_threshold(self.eng.ctx, self.handle, int(bool(soft)), thr.ctypes.data_as(_dp)))
+        return thr
+
+    def energy(self, level):
+        out = np.empty(self.shape()[0])
+        with self.eng._call_lock:
+            self.eng._bind_stream()
+            self.eng._check(self.eng.lib.vw_result_energy(self.eng.ctx, self.handle, int(level), out.ctypes.data_as(_dp)))
+        return out
+
+    def reconstruct(self, hs, gs, mode, align=None, order=ORDER_SPLIT, detail_mask=None, use_approx=True, out=None, flags=0):
+        b, n, j = self.shape()
+        hs, gs = _fp(hs), _fp(gs)
+        res = out if out is not None else np.empty((b, n))
+        if detail_mask is None:
+            detail_mask = (1 << j) - 1
+        al = Engine._align_array(align, j)
+        with self.eng._call_lock:
+            fl = self.eng._bind_stream(res) | flags
+            self.eng._check(self.eng.lib.vw_modwt_reconstruct_h(self.eng.ctx, self.handle, hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp),
+                                                                hs.size, int(mode), al, int(order), C.c_uint64(detail_mask),
+                                                                int(bool(use_approx)), _vp(_ptr(res)), _ld(res), fl))
+        return res
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.vw_result_free(self.eng.ctx, self.handle)
+            self.handle = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiEngine:
+    """Several GPUs driven by ONE host thread (vw_init_multi): what a JVM caller uses for a span-sharded long signal.
+    Buffers are torch CUDA tensors here, one list entry per device."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self.handle = _vp()
+        rc = self.lib.vw_init_multi(arr, len(self.devices), C.byref(self.handle))
+        if rc != VW_OK:
+            raise NativeEngineError(f"vw_init_multi({self.devices}) failed with {self.lib.vw_status_name(rc).decode()}")
+
+    def _check(self, rc):
+        if rc != VW_OK:
+            msg = self.lib.vw_multi_last_error(self.handle).decode(errors="replace")
+            exc, code = _STATUS.get(rc, (NativeEngineError, None))
+            raise exc(f"[{code.value}] {msg}", code) if code is not None else exc(f"{self.lib.vw_status_name(rc).decode()}: {msg}")
+
+    @staticmethod
+    def _ptrs(tensors):
+        return (_vp * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def forward(self, plan, xext, hs, gs, mode, w, v, timed=False, flags=0):
+        hs, gs = _fp(hs), _fp(gs)
+        ms = C.c_float(0.0)
+        self._check(self.lib.vw_modwt_forward_sharded(self.handle, C.byref(plan), self._ptrs(xext), hs.ctypes.data_as(_dp),
+                                                      gs.ctypes.data_as(_dp), int(mode), self._ptrs(w), w[0].stride(0),
+                                                      self._ptrs(v), C.byref(ms) if timed else None, flags))
+        return float(ms.value) if timed else None
+
+    def inverse(self, plan, w, v, hs, gs, mode, order, xout, timed=False, flags=0):
+        hs, gs = _fp(hs), _fp(gs)
+        ms = C.c_float(0.0)
+        self._check(self.lib.vw_modwt_inverse_sharded(self.handle, C.byref(plan), self._ptrs(w), w[0].stride(0), self._ptrs(v),
+                                                      hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), int(mode), int(order),
+                                                      self._ptrs(xout), C.byref(ms) if timed else None, flags))
+        return float(ms.value) if timed else None
+
+    def synchronize(self):
+        self._check(self.lib.vw_multi_synchronize(self.handle))
+
+    def launch_count(self):
+        return sum(int(self.lib.vw_launch_count(_vp(self.lib.vw_multi_ctx(self.handle, r)))) for r in range(len(self.devices)))
+
+    def close(self):
+        if self.handle:
+            self.lib.vw_destroy_multi(self.handle)
+            self.handle = _vp()

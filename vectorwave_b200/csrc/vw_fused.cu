@@ -791,9 +791,15 @@ int prefetch_distance(vw_ctx *ctx, const void *func, int nthreads, size_t smem, 
 int64_t even_up(int64_t v) { return (v + 1) & ~1ll; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage) {
-    if (fwd) return (size_t)((2 * (tile + htot) + (use_stage ? 2 * tile : 0)) * 8 + 64 + kTapBytes);
-    return (size_t)(4 * (tile + htot) * 8 + 64 + kTapBytes);
+// `slack`: doubles behind every tile buffer of the lean kernels (vw_lean.cu: items overshoot their range by < R * d)
+size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage, int64_t slack = 0) {
+    if (fwd) return (size_t)((2 * (tile + htot + slack) + (use_stage ? 2 * tile : 0)) * 8 + 64 + kTapBytes);
+    return (size_t)(4 * (tile + htot + slack) * 8 + 64 + kTapBytes);
+}
+// does the planner have to budget for the lean kernels' slack?  (quadrature-mirror pairs are assumed from 16 taps on)
+int64_t lean_slack(const vw_ctx *ctx, int l, int first, int nf) {
+    const bool lean = (l <= 12 && !(l & 1) && (ctx->opt_lean & 1)) || ((l == 16 || l == 18 || l == 20) && (ctx->opt_lean & 2));
+    return lean && nf <= 6 ? (int64_t)kR * ((int64_t)1 << (first - 1 + nf - 1)) : 0;
 }
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
@@ -803,9 +809,9 @@ double tile_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t 
     const int64_t hexact = (int64_t)(l - 1) * d0 * ((1ll << nf) - 1);
     const int64_t htot = even_up(hexact);
     const bool use_stage = fwd && d0 < 4 && VW_STAGE_W;
-    const size_t smem = smem_bytes(fwd, t, htot, use_stage);
+    const size_t smem = smem_bytes(fwd, t, htot, use_stage, lean_slack(ctx, l, first, nf));
     if (smem > ctx->smem_optin - 1024) return INFINITY;
-    const int regs = l <= VW_LB4_MAXL ? 64 : (l <= 12 ? 85 : 128);
+    const int regs = lean_slack(ctx, l, first, nf) > 0 ? 85 : (l <= VW_LB4_MAXL ? 64 : (l <= 12 ? 85 : 128));
     int64_t ctas = std::min<int64_t>((int64_t)(228 * 1024) / (int64_t)(smem + 1024), 65536 / (regs * nthreads));
     ctas = std::min<int64_t>(ctas, 8);
     if (ctas < 1) return INFINITY;

@@ -32,7 +32,7 @@ struct LeanFwd {
     double *w; long long ldw, lsw;
     double *v; long long ldv;
     long long n_in, t0, n_out;
-    int tile, htot, pbuf, nlev, log2d0, mode, tiles_per_row, use_stage, pf_dist, batch;
+    int tile, htot, pbuf, nlev, log2d0, mode, tiles_per_row, use_stage, stage_all, pf_dist, batch;
     int ra[kMaxLev];      // first tile-buffer index computed at each level (a multiple of 2d below htot)
     int items[kMaxLev];   // items (chunks x phases) of each level
     double h[VW_LEAN_MAX_L], g[VW_LEAN_MAX_L];
@@ -53,15 +53,27 @@ __device__ __forceinline__ double tap_g(const double (&h)[VW_LEAN_MAX_L], const 
     return QMF ? ((k & 1) ? -h[L - 1 - k] : h[L - 1 - k]) : g[k];
 }
 
+// shared memory by BYTE offset: one integer instruction per access (an element index costs a second one for the scaling)
+__device__ __forceinline__ double lds_b(int byte_off) {
+    return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(lean_smem) + byte_off);
+}
+__device__ __forceinline__ void sts_b(int byte_off, double v) {
+    *reinterpret_cast<double *>(reinterpret_cast<char *>(lean_smem) + byte_off) = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // analysis
 // ------------------------------------------------------------------------------------------------
-// shared memory (doubles): [buf0: pbuf][buf1: pbuf][stg0: tile][stg1: tile] (stg only when use_stage), then one mbarrier
+// shared memory (doubles): [buf0: pbuf][buf1: pbuf][stg0: tile][stg1: tile] (stg only when use_stage), then one mbarrier.
+// Detail rows of dilation 1 / 2 always leave through a staging buffer and ONE bulk store (8-byte global stores at those
+// strides would be partial-sector writes).  With stage_all (groups that start at level 1, where the two staging buffers
+// exist anyway) every level does: levels alternate between the buffers, thread 0 makes sure the store issued two levels
+// earlier has read its buffer before anybody rewrites it -- two instructions per coefficient instead of three to five
+// for a strided 64-bit global store, and HBM only ever sees whole contiguous rows.
 template <int L, bool QMF>
-__global__ void __launch_bounds__(256, 3) k_lean_analysis(const __grid_constant__ LeanFwd a) {
+__global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __grid_constant__ LeanFwd a) {
     const int T = a.tile, HT = a.htot, PB = a.pbuf;
-    const int o_stg0 = 2 * PB, o_stg1 = o_stg0 + (a.use_stage ? T : 0);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(lean_smem + o_stg1 + (a.use_stage ? T : 0));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(lean_smem + 2 * PB + (a.use_stage ? 2 * T : 0));
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const long long b = blockIdx.y;
@@ -69,11 +81,10 @@ __global__ void __launch_bounds__(256, 3) k_lean_analysis(const __grid_constant_
     const long long rem = a.t0 + a.n_out - g0;
     const int Tt = (int)(rem < T ? rem : T);                     // owned samples of this tile
     const int PP = HT + Tt;                                      // valid extent of the tile buffers
-    const double *xrow = a.x + b * a.ldx;
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
-    stage_tile(lean_smem, xrow, g0 - HT, PP, a.n_in, a.mode, true, bar, false);
+    stage_tile(lean_smem, a.x + b * a.ldx, g0 - HT, PP, a.n_in, a.mode, true, bar, false);
     if (a.pf_dist > 0 && tid == 32) {
         // the CTA that will inherit this slot: its input tile goes to L2 now (see vw_fused.cu)
         const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
@@ -86,28 +97,27 @@ __global__ void __launch_bounds__(256, 3) k_lean_analysis(const __grid_constant_
     mbar_wait(bar, 0);
     if (a.mode != VW_PERIODIC) __syncthreads();   // hand-filled samples of the open ends
 
-    int cur = 0, nxt = PB;
+    int cur8 = 0, nxt8 = PB * 8;                  // byte offsets of the ping-pong buffers
+    const int stg8 = 2 * PB * 8;
     for (int lev = 0; lev < a.nlev; lev++) {
         const int ld2 = a.log2d0 + lev;
-        const int d = 1 << ld2;
-        const bool last = lev + 1 == a.nlev;
-        const bool staged = a.use_stage && ld2 < 2;
-        const int o_stg = (lev & 1) ? o_stg1 : o_stg0;
-        double *wrow = a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0);   // W_lev[owned region]; uniform per CTA
+        const int d8 = 8 << ld2;
+        const int ostg8 = stg8 + (lev & 1) * T * 8;
+        const bool staged = a.stage_all || (a.use_stage && ld2 < 2);
         const int ra = a.ra[lev];
         const int items = a.items[lev];
         for (int wi = tid; wi < items; wi += (int)blockDim.x) {
-            const int c = wi >> ld2, ph = wi & (d - 1);
+            const int c = wi >> ld2, ph = wi & ((1 << ld2) - 1);
             const int base = ra + ((c * kR) << ld2) + ph;
             double ah[kR], ag[kR];
 #pragma unroll
             for (int r = 0; r < kR; r++) { ah[r] = 0.0; ag[r] = 0.0; }
             {
-                int p = cur + base + ((kR - 1) << ld2);
+                int p = cur8 + base * 8 + (kR - 1) * d8;
 #pragma unroll
                 for (int m = kR - 1; m >= -(L - 1); m--) {   // descending m => ascending tap index per output
-                    const double xv = lean_smem[p];
-                    p -= d;
+                    const double xv = lds_b(p);
+                    p -= d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
                         const int k = r - m;
@@ -120,46 +130,48 @@ __global__ void __launch_bounds__(256, 3) k_lean_analysis(const __grid_constant_
             }
             // V_lev: unconditional (overshoot lands in the slack behind the tile)
             {
-                int q = nxt + base;
+                int q = nxt8 + base * 8;
 #pragma unroll
-                for (int r = 0; r < kR; r++) { lean_smem[q] = ah[r]; q += d; }
+                for (int r = 0; r < kR; r++) { sts_b(q, ah[r]); q += d8; }
             }
-            // W_lev: only owned outputs, tile indices [HT, PP)
+            // W_lev: owned outputs only, tile indices [HT, HT + T) (a ragged last tile stages a little garbage behind
+            // its Tt samples; the bulk store moves Tt)
             const int rel = base - HT;
-            const int rlo = rel >= 0 ? 0 : (-rel + d - 1) >> ld2;
-            int rhi = (PP - base + d - 1) >> ld2;
-            rhi = rhi < kR ? rhi : kR;
             if (staged) {
-                int q = o_stg + rel;
-                if (rlo == 0 && rhi == kR) {
+                int q = ostg8 + rel * 8;
+                if (rel >= 0 && rel + (kR - 1) * (d8 >> 3) < T) {
 #pragma unroll
-                    for (int r = 0; r < kR; r++) { lean_smem[q] = ag[r]; q += d; }
+                    for (int r = 0; r < kR; r++) { sts_b(q, ag[r]); q += d8; }
                 } else {
+                    int pos = rel;
 #pragma unroll
-                    for (int r = 0; r < kR; r++) { if (r >= rlo && r < rhi) lean_smem[q] = ag[r]; q += d; }
+                    for (int r = 0; r < kR; r++) { if (pos >= 0 && pos < T) sts_b(q, ag[r]); q += d8; pos += d8 >> 3; }
                 }
             } else {
-                if (rlo == 0 && rhi == kR) {
+                // dilation >= 4: lanes hold consecutive samples, every warp store writes whole 32-byte sectors
+                char *wq = reinterpret_cast<char *>(a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0) + rel);
+                if (rel >= 0 && rel + (kR - 1) * (d8 >> 3) < Tt) {
 #pragma unroll
-                    for (int r = 0; r < kR; r++) wrow[rel + (r << ld2)] = ag[r];
+                    for (int r = 0; r < kR; r++) { *reinterpret_cast<double *>(wq) = ag[r]; wq += d8; }
                 } else {
+                    int pos = rel;
 #pragma unroll
-                    for (int r = 0; r < kR; r++) if (r >= rlo && r < rhi) wrow[rel + (r << ld2)] = ag[r];
+                    for (int r = 0; r < kR; r++) { if (pos >= 0 && pos < Tt) *reinterpret_cast<double *>(wq) = ag[r]; wq += d8; pos += d8 >> 3; }
                 }
             }
         }
-        if (staged || last) fence_async_smem();   // generic-proxy writes a bulk store is about to read
+        if (staged || lev + 1 == a.nlev) fence_async_smem();   // generic-proxy writes a bulk store is about to read
+        // stage_all: the buffer the NEXT level stages into was handed to a bulk store one level ago -- it must have been read
+        if (a.stage_all && tid == 0) bulk_wait_read<0>();
         __syncthreads();
         if (staged && tid == 0) {
-            // at most two staged levels per group (dilation 1 and 2), each with its own buffer: nothing is rewritten, the
-            // bulk store drains while the next level computes
-            bulk_s2g(wrow, lean_smem + o_stg, (uint32_t)Tt * 8u);
+            bulk_s2g(a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0), lean_smem + (ostg8 >> 3), (uint32_t)Tt * 8u);
             bulk_commit();
         }
-        const int t = cur; cur = nxt; nxt = t;
+        const int t = cur8; cur8 = nxt8; nxt8 = t;
     }
     if (tid == 0) {
-        bulk_s2g(a.v + b * a.ldv + (g0 - a.t0), lean_smem + cur + HT, (uint32_t)Tt * 8u);
+        bulk_s2g(a.v + b * a.ldv + (g0 - a.t0), lean_smem + (cur8 >> 3) + HT, (uint32_t)Tt * 8u);
         bulk_commit();
         bulk_wait_read<0>();
     }
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(256, 3) k_lean_analysis(const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // shared memory (doubles): [bufA: pbuf][bufB: pbuf][W0: pbuf][W1: pbuf], then three mbarriers (V, W0, W1)
 template <int L, bool QMF>
-__global__ void __launch_bounds__(256, 3) k_lean_synthesis(const __grid_constant__ LeanInv a) {
+__global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const __grid_constant__ LeanInv a) {
     const int T = a.tile, PB = a.pbuf;
     uint64_t *bars = reinterpret_cast<uint64_t *>(lean_smem + 4 * PB);
     const int tid = threadIdx.x;
@@ -205,7 +217,7 @@ __global__ void __launch_bounds__(256, 3) k_lean_synthesis(const __grid_constant
     mbar_wait(&bars[0], 0);
     uint32_t wphase0 = 0, wphase1 = 0;
 
-    int cur = 0, nxt = PB;
+    int cur8 = 0, nxt8 = PB * 8;
     for (int lev = top; lev >= 0; lev--) {
         const int slot = lev & 1;
         if (lev > 0) stage_w(lev - 1, slot ^ 1);   // the next level's details land while this one computes
@@ -214,26 +226,25 @@ __global__ void __launch_bounds__(256, 3) k_lean_synthesis(const __grid_constant
         // hand-filled samples (zero padding) of this level's tiles were written before the previous level's closing
         // barrier; only the first level's were written just now
         if (lev == top && a.mode != VW_PERIODIC) __syncthreads();
-        const int wof = (2 + slot) * PB;
+        const int wof8 = (2 + slot) * PB * 8;
         const int ld2 = a.log2d0 + lev;
-        const int d = 1 << ld2;
+        const int d8 = 8 << ld2;
         const int M = Tt + (lev > 0 ? a.ext[lev - 1] : 0);      // outputs of this level
-        const int Q = (M + d - 1) >> ld2;
-        const int chunks = (Q + kR - 1) / kR;
-        const int items = chunks << ld2;
+        const int Q = (M + (1 << ld2) - 1) >> ld2;
+        const int items = ((Q + kR - 1) / kR) << ld2;
         for (int wi = tid; wi < items; wi += (int)blockDim.x) {
-            const int c = wi >> ld2, ph = wi & (d - 1);
-            const int base = ((c * kR) << ld2) + ph;
+            const int c = wi >> ld2, ph = wi & ((1 << ld2) - 1);
+            const int base8 = (((c * kR) << ld2) + ph) * 8;
             double acc[kR];
 #pragma unroll
             for (int r = 0; r < kR; r++) acc[r] = 0.0;
             // all H taps, then all G taps (MultiLevelMODWTTransform.java:578-589); overshoot outputs read slack
             {
-                int p = cur + base;
+                int p = cur8 + base8;
 #pragma unroll
                 for (int m = 0; m <= kR + L - 2; m++) {
-                    const double xv = lean_smem[p];
-                    p += d;
+                    const double xv = lds_b(p);
+                    p += d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
                         const int k = m - r;
@@ -242,11 +253,11 @@ __global__ void __launch_bounds__(256, 3) k_lean_synthesis(const __grid_constant
                 }
             }
             {
-                int p = wof + base;
+                int p = wof8 + base8;
 #pragma unroll
                 for (int m = 0; m <= kR + L - 2; m++) {
-                    const double xw = lean_smem[p];
-                    p += d;
+                    const double xw = lds_b(p);
+                    p += d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
                         const int k = m - r;
@@ -254,16 +265,16 @@ __global__ void __launch_bounds__(256, 3) k_lean_synthesis(const __grid_constant
                     }
                 }
             }
-            int q = nxt + base;
+            int q = nxt8 + base8;
 #pragma unroll
-            for (int r = 0; r < kR; r++) { lean_smem[q] = acc[r]; q += d; }
+            for (int r = 0; r < kR; r++) { sts_b(q, acc[r]); q += d8; }
         }
         fence_async_smem();   // order this level's generic-proxy traffic before later bulk copies touch the buffers
         __syncthreads();
-        const int t = cur; cur = nxt; nxt = t;
+        const int t = cur8; cur8 = nxt8; nxt8 = t;
     }
     if (tid == 0) {
-        bulk_s2g(a.out + b * a.ldo + g0, lean_smem + cur, (uint32_t)Tt * 8u);
+        bulk_s2g(a.out + b * a.ldo + g0, lean_smem + (cur8 >> 3), (uint32_t)Tt * 8u);
         bulk_commit();
         bulk_wait_read<0>();
     }
@@ -338,6 +349,7 @@ int vw_lean_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt32 &f, int64_t
     a.n_in = p.n_in; a.t0 = p.t0; a.n_out = p.n_out; a.batch = (int)p.batch;
     a.tile = (int)tile; a.htot = (int)htot; a.nlev = p.nlevels; a.log2d0 = p.first_level - 1; a.mode = p.mode;
     a.tiles_per_row = (int)tiles_per_row; a.use_stage = use_stage;
+    a.stage_all = use_stage && p.l <= 12;   // short filters are issue-bound: see the kernel comment
     const int64_t d0 = 1ll << (p.first_level - 1);
     const int64_t dmax = d0 << (p.nlevels - 1);
     const int64_t pbuf = ((tile + htot + kR * dmax) + 1) & ~1ll;   // slack: an item overshoots its level's range by < R*d

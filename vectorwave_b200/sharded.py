@@ -104,6 +104,13 @@ class SpanShardedMODWT:
         self.pad = total_i if self.upfront else max(self.halo_i)
         self.lead = total_f if self.upfront else max(self.halo_f)
         self.lead_w = self.rf[0] if self.upfront else 0     # W rows carry the not-yet-final left part of each level
+        # Default case (the engine's own launch groups, up-front schedule): layout and cascades live below the C ABI
+        # (vw_span_plan_query + vw_modwt_{forward,inverse}_span_all); this class only moves the halos between ranks.
+        # Caller-chosen groups and the per-group schedule keep the Python schedules below.
+        self.plan = None
+        if self.upfront and groups_forward is None and groups_inverse is None:
+            self.plan = _native.span_plan(self.l, self.levels, self.n_local, self.world)
+            self.lead, self.lead_w, self.pad = int(self.plan.lead), int(self.plan.lead_w), int(self.plan.pad)
 
     def _eng(self):
         if self.engine is None:
@@ -148,6 +155,43 @@ class SpanShardedMODWT:
             bufs = [torch.empty(length, dtype=torch.float64, device=dev) for _ in range(count)]
             cache[key] = bufs
         return bufs
+
+    # -- default path: one ABI call per direction around one exchange ------------------------------------------
+    def _forward_plan(self, x_local, result=None):
+        n, dev, p = self.n_local, x_local.device, self.plan
+        row = self.lead_w + n + self.pad
+        if result is not None and result.storage is not None and tuple(result.storage.shape) == (self.levels, row):
+            wfull, vstore = result.storage, result.v
+        else:
+            wfull = torch.empty((self.levels, row), dtype=torch.float64, device=dev)
+            vstore = torch.empty(n + self.pad, dtype=torch.float64, device=dev)
+        (xext,) = self._scratch("xext", 1, self.lead + n, dev)
+        xext[self.lead:].copy_(x_local)
+        self.exchange_forward(xext)
+        self._eng().forward_span_all(xext, p, self.hs, self.gs, wfull, vstore)
+        return SpanResult(wfull[:, self.lead_w:], vstore, n, self.pad, storage=wfull)
+
+    def exchange_forward(self, xext):
+        """The analysis halo: my last `lead` samples -> right neighbour's lead area (ring wrap / zeros at the open end)."""
+        if self.lead > 0:
+            self._exchange(xext[self.n_local:].contiguous(), xext[:self.lead], to_right=True)
+
+    def exchange_inverse(self, result):
+        """The synthesis halo: the first samples of V_J and of every W_j row -> left neighbour's pad areas."""
+        p, dev = self.plan, result.v.device
+        if int(p.inverse_msg) == 0:
+            return
+        send, recv = self._scratch("msg", 2, int(p.inverse_msg), dev)
+        eng = self._eng()
+        eng.span_pack_inverse(p, result.storage, result.v, send)
+        self._exchange(send, recv, to_right=False)
+        eng.span_unpack_inverse(p, recv, result.storage, result.v)
+
+    def _inverse_plan(self, result, order):
+        self.exchange_inverse(result)
+        out = torch.empty(self.n_local, dtype=torch.float64, device=result.v.device)
+        self._eng().inverse_span_all(self.plan, result.storage, result.v, self.hrs, self.grs, order, out)
+        return out
 
     def _forward_upfront(self, x_local, result=None):
         """One exchange of the total left halo, then every group on [-(halo still needed later), n)."""
@@ -214,6 +258,8 @@ class SpanShardedMODWT:
         n, dev = self.n_local, x_local.device
         if x_local.numel() != n:
             raise IllegalArgumentException(f"expected a span of {n} samples, got {x_local.numel()}")
+        if self.plan is not None:
+            return self._forward_plan(x_local, result)
         if self.upfront:
             return self._forward_upfront(x_local, result)
         eng = self._eng()
@@ -240,6 +286,8 @@ class SpanShardedMODWT:
 
     # -- synthesis ------------------------------------------------------------------------------------------
     def inverse(self, result, order=ORDER_SPLIT):
+        if self.plan is not None:
+            return self._inverse_plan(result, order)
         if self.upfront:
             return self._inverse_upfront(result, order)
         n, dev = self.n_local, result.v.device
