@@ -81,6 +81,7 @@ struct vw_ctx {
     struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
     std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
     int64_t opt_lean = 3;    // issue-lean tile kernels (vw_lean.cu): bit 0 = filters up to 12 taps, bit 1 = 16..20-tap quadrature-mirror pairs
+    int64_t opt_lean_small = 1;   // lean short filters: 128-thread CTAs on ~1024-sample tiles (vw_fused.cu: lean_small_tiles)
     int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
     std::recursive_mutex mu;   // every public entry point holds it: calls on one ctx from several host threads serialise
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;

@@ -53,12 +53,17 @@ __device__ __forceinline__ double tap_g(const double (&h)[VW_LEAN_MAX_L], const 
     return QMF ? ((k & 1) ? -h[L - 1 - k] : h[L - 1 - k]) : g[k];
 }
 
-// shared memory by BYTE offset: one integer instruction per access (an element index costs a second one for the scaling)
-__device__ __forceinline__ double lds_b(int byte_off) {
-    return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(lean_smem) + byte_off);
+// Shared memory by 32-bit shared-window ADDRESS (byte address with the window base already folded in): one integer
+// instruction per access.  Through a C++ pointer the compiler re-adds the base of `lean_smem` to the offset at every
+// access (two IMADs per LDS / STS in the SASS).  "memory" clobber, not volatile: the accesses keep their order relative
+// to barriers and to each other, the FMAs around them schedule freely.
+__device__ __forceinline__ double lds_a(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
-__device__ __forceinline__ void sts_b(int byte_off, double v) {
-    *reinterpret_cast<double *>(reinterpret_cast<char *>(lean_smem) + byte_off) = v;
+__device__ __forceinline__ void sts_a(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -97,12 +102,13 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
     mbar_wait(bar, 0);
     if (a.mode != VW_PERIODIC) __syncthreads();   // hand-filled samples of the open ends
 
-    int cur8 = 0, nxt8 = PB * 8;                  // byte offsets of the ping-pong buffers
-    const int stg8 = 2 * PB * 8;
+    const uint32_t sbase = smem_u32(lean_smem);
+    uint32_t cur8 = sbase, nxt8 = sbase + PB * 8;   // shared-window addresses of the ping-pong buffers
+    const uint32_t stg8 = sbase + 2 * PB * 8;
     for (int lev = 0; lev < a.nlev; lev++) {
         const int ld2 = a.log2d0 + lev;
         const int d8 = 8 << ld2;
-        const int ostg8 = stg8 + (lev & 1) * T * 8;
+        const uint32_t ostg8 = stg8 + (lev & 1) * T * 8;
         const bool staged = a.stage_all || (a.use_stage && ld2 < 2);
         const int ra = a.ra[lev];
         const int items = a.items[lev];
@@ -113,10 +119,10 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
 #pragma unroll
             for (int r = 0; r < kR; r++) { ah[r] = 0.0; ag[r] = 0.0; }
             {
-                int p = cur8 + base * 8 + (kR - 1) * d8;
+                uint32_t p = cur8 + base * 8 + (kR - 1) * d8;
 #pragma unroll
                 for (int m = kR - 1; m >= -(L - 1); m--) {   // descending m => ascending tap index per output
-                    const double xv = lds_b(p);
+                    const double xv = lds_a(p);
                     p -= d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
@@ -130,22 +136,22 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
             }
             // V_lev: unconditional (overshoot lands in the slack behind the tile)
             {
-                int q = nxt8 + base * 8;
+                uint32_t q = nxt8 + base * 8;
 #pragma unroll
-                for (int r = 0; r < kR; r++) { sts_b(q, ah[r]); q += d8; }
+                for (int r = 0; r < kR; r++) { sts_a(q, ah[r]); q += d8; }
             }
             // W_lev: owned outputs only, tile indices [HT, HT + T) (a ragged last tile stages a little garbage behind
             // its Tt samples; the bulk store moves Tt)
             const int rel = base - HT;
             if (staged) {
-                int q = ostg8 + rel * 8;
+                uint32_t q = ostg8 + rel * 8;
                 if (rel >= 0 && rel + (kR - 1) * (d8 >> 3) < T) {
 #pragma unroll
-                    for (int r = 0; r < kR; r++) { sts_b(q, ag[r]); q += d8; }
+                    for (int r = 0; r < kR; r++) { sts_a(q, ag[r]); q += d8; }
                 } else {
                     int pos = rel;
 #pragma unroll
-                    for (int r = 0; r < kR; r++) { if (pos >= 0 && pos < T) sts_b(q, ag[r]); q += d8; pos += d8 >> 3; }
+                    for (int r = 0; r < kR; r++) { if (pos >= 0 && pos < T) sts_a(q, ag[r]); q += d8; pos += d8 >> 3; }
                 }
             } else {
                 // dilation >= 4: lanes hold consecutive samples, every warp store writes whole 32-byte sectors
@@ -165,13 +171,13 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
         if (a.stage_all && tid == 0) bulk_wait_read<0>();
         __syncthreads();
         if (staged && tid == 0) {
-            bulk_s2g(a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0), lean_smem + (ostg8 >> 3), (uint32_t)Tt * 8u);
+            bulk_s2g(a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0), lean_smem + ((ostg8 - sbase) >> 3), (uint32_t)Tt * 8u);
             bulk_commit();
         }
-        const int t = cur8; cur8 = nxt8; nxt8 = t;
+        const uint32_t t = cur8; cur8 = nxt8; nxt8 = t;
     }
     if (tid == 0) {
-        bulk_s2g(a.v + b * a.ldv + (g0 - a.t0), lean_smem + (cur8 >> 3) + HT, (uint32_t)Tt * 8u);
+        bulk_s2g(a.v + b * a.ldv + (g0 - a.t0), lean_smem + ((cur8 - sbase) >> 3) + HT, (uint32_t)Tt * 8u);
         bulk_commit();
         bulk_wait_read<0>();
     }
@@ -217,7 +223,8 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
     mbar_wait(&bars[0], 0);
     uint32_t wphase0 = 0, wphase1 = 0;
 
-    int cur8 = 0, nxt8 = PB * 8;
+    const uint32_t sbase = smem_u32(lean_smem);
+    uint32_t cur8 = sbase, nxt8 = sbase + PB * 8;
     for (int lev = top; lev >= 0; lev--) {
         const int slot = lev & 1;
         if (lev > 0) stage_w(lev - 1, slot ^ 1);   // the next level's details land while this one computes
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
         // hand-filled samples (zero padding) of this level's tiles were written before the previous level's closing
         // barrier; only the first level's were written just now
         if (lev == top && a.mode != VW_PERIODIC) __syncthreads();
-        const int wof8 = (2 + slot) * PB * 8;
+        const uint32_t wof8 = sbase + (2 + slot) * PB * 8;
         const int ld2 = a.log2d0 + lev;
         const int d8 = 8 << ld2;
         const int M = Tt + (lev > 0 ? a.ext[lev - 1] : 0);      // outputs of this level
@@ -240,10 +247,10 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
             for (int r = 0; r < kR; r++) acc[r] = 0.0;
             // all H taps, then all G taps (MultiLevelMODWTTransform.java:578-589); overshoot outputs read slack
             {
-                int p = cur8 + base8;
+                uint32_t p = cur8 + base8;
 #pragma unroll
                 for (int m = 0; m <= kR + L - 2; m++) {
-                    const double xv = lds_b(p);
+                    const double xv = lds_a(p);
                     p += d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
@@ -253,10 +260,10 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
                 }
             }
             {
-                int p = wof8 + base8;
+                uint32_t p = wof8 + base8;
 #pragma unroll
                 for (int m = 0; m <= kR + L - 2; m++) {
-                    const double xw = lds_b(p);
+                    const double xw = lds_a(p);
                     p += d8;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
@@ -265,16 +272,16 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
                     }
                 }
             }
-            int q = nxt8 + base8;
+            uint32_t q = nxt8 + base8;
 #pragma unroll
-            for (int r = 0; r < kR; r++) { sts_b(q, acc[r]); q += d8; }
+            for (int r = 0; r < kR; r++) { sts_a(q, acc[r]); q += d8; }
         }
         fence_async_smem();   // order this level's generic-proxy traffic before later bulk copies touch the buffers
         __syncthreads();
-        const int t = cur8; cur8 = nxt8; nxt8 = t;
+        const uint32_t t = cur8; cur8 = nxt8; nxt8 = t;
     }
     if (tid == 0) {
-        bulk_s2g(a.out + b * a.ldo + g0, lean_smem + (cur8 >> 3), (uint32_t)Tt * 8u);
+        bulk_s2g(a.out + b * a.ldo + g0, lean_smem + ((cur8 - sbase) >> 3), (uint32_t)Tt * 8u);
         bulk_commit();
         bulk_wait_read<0>();
     }

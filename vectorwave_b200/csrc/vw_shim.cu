@@ -552,6 +552,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "wave")) ctx->opt_wave = value;
     else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
     else if (!strcmp(name, "lean")) ctx->opt_lean = value;
+    else if (!strcmp(name, "lean_small")) ctx->opt_lean_small = value;
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;       // event pair around every public call (vw_last_timing)
     else return vw_fail(ctx, VW_EINVAL, "unknown option '%s'", name);

@@ -187,6 +187,14 @@ class SpanShardedMODWT:
         self._exchange(send, recv, to_right=False)
         eng.span_unpack_inverse(p, recv, result.storage, result.v)
 
+    def exchange_only(self, result):
+        """Both directions' halo exchanges without the cascades (bench.py times this separately)."""
+        if self.plan is None:
+            raise IllegalArgumentException("exchange_only needs the default (plan) schedule")
+        (xext,) = self._scratch("xext", 1, self.lead + self.n_local, result.v.device)
+        self.exchange_forward(xext)
+        self.exchange_inverse(result)
+
     def _inverse_plan(self, result, order):
         self.exchange_inverse(result)
         out = torch.empty(self.n_local, dtype=torch.float64, device=result.v.device)
@@ -315,76 +323,3 @@ class SpanShardedMODWT:
             vext = work[cur]
             cur ^= 1
         return out
-
-
-def bench_span(args, rank, world, local_rank, metric, unit, ClockSampler, measured_peaks):
-    """bench.py --workload span: BASELINE.json configs[3], one 2^28-sample coif5 J=10 PERIODIC signal span-sharded over
-    the ranks (strong scaling: the signal is fixed, each rank owns N/P samples)."""
-    import json
-
-    import vectorwave_b200 as vw
-
-    n_total, levels = 1 << 28, 10
-    n_local = n_total // world
-    dev = torch.device("cuda", local_rank)
-    wv = vw.Coiflet.COIF5
-    sh = SpanShardedMODWT(wv, levels, n_local, BoundaryMode.PERIODIC, rank=rank, world=world,
-                          engine=Engine.get(local_rank))
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(42 + rank)
-    x = torch.randn(n_local, dtype=torch.float64, device=dev, generator=gen)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    res = None
-    for _ in range(max(args.warmup, 3)):
-        res = sh.forward(x)
-        xr = sh.inverse(res)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    eng = sh.engine
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        res = sh.forward(x, result=res)
-        xr = sh.inverse(res)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms.item()) / args.steps
-    launches = eng.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    rt = float((xr - x).abs().max())
-    peak, peak_src = measured_peaks()
-    if rank == 0:
-        value = n_total / ms_step * 1e-6
-        model = peak / (48.0 * levels)
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "single2p28_coif5_J10", "wavelet": "coif5", "signal_length": n_total,
-                           "levels": levels, "boundary": "PERIODIC",
-                           "sharding": f"contiguous spans of {n_local} samples, NCCL send/recv halo exchange per launch group "
-                                       f"(forward groups {sh.gf}, inverse groups {sh.gi})",
-                           "l2": "per-rank working set 24 GiB / world, far larger than L2"},
-                "roofline": {"bound": "hbm", "kernel": "k_fused_analysis / k_column_analysis", "peak": peak, "unit": "GB/s",
-                             "achieved": 48.0 * levels * n_total / world / ms_step * 1e-6,
-                             "frac": 48.0 * levels * n_total / world / ms_step * 1e-6 / peak, "traffic": None,
-                             "peak_source": peak_src,
-                             "note": "whole step (forward + inverse) per GPU: 48*J algorithmic bytes per sample"},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
-                "round_trip_max_abs_err": rt, "roofline_model_gsamples": model * world,
-                "frac_of_roofline_model": value / (model * world)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
