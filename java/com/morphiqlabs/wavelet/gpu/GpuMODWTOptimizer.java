@@ -98,7 +98,10 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
         int b = signals.length, n = signals[0].length;
         double[] hs = scaled(wavelet.lowPassDecomposition()), gs = scaled(wavelet.highPassDecomposition());
         long bytes = (long) b * n * 8;
-        MemorySegment x = VwNative.allocPinned(bytes), w = VwNative.allocPinned(bytes), v = VwNative.allocPinned(bytes);
+        PinnedArena pin = PinnedArena.current();      // pooled: cudaMallocHost per call would cost more than the transform
+        pin.reset();
+        MemorySegment[] seg = pin.takeAll(bytes, bytes, bytes);
+        MemorySegment x = seg[0], w = seg[1], v = seg[2];
         try (Arena a = Arena.ofConfined()) {
             for (int i = 0; i < b; i++) MemorySegment.copy(signals[i], 0, x, ValueLayout.JAVA_DOUBLE, (long) i * n * 8, n);
             MemorySegment hseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, hs), gseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, gs);
@@ -110,8 +113,6 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
             return out;
         } catch (Throwable t) {
             throw VwNative.rethrow(t);
-        } finally {
-            VwNative.freePinned(x); VwNative.freePinned(w); VwNative.freePinned(v);
         }
     }
 
@@ -120,7 +121,10 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
         double[] detail = waveletCoeffs, approx = scalingCoeffs;
         int n = approx.length;
         double[] hs = scaled(wavelet.lowPassReconstruction()), gs = scaled(wavelet.highPassReconstruction());
-        MemorySegment w = VwNative.allocPinned(n * 8L), v = VwNative.allocPinned(n * 8L), x = VwNative.allocPinned(n * 8L);
+        PinnedArena pin = PinnedArena.current();
+        pin.reset();
+        MemorySegment[] seg = pin.takeAll(n * 8L, n * 8L, n * 8L);
+        MemorySegment w = seg[0], v = seg[1], x = seg[2];
         try (Arena a = Arena.ofConfined()) {
             VwNative.copyIn(w, detail);
             VwNative.copyIn(v, approx);
@@ -133,8 +137,6 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
             return VwNative.copyOut(x, 0, n);
         } catch (Throwable t) {
             throw VwNative.rethrow(t);
-        } finally {
-            VwNative.freePinned(w); VwNative.freePinned(v); VwNative.freePinned(x);
         }
     }
 
@@ -145,7 +147,10 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
         if (soaDetailPerLevel.length != levels) throw new IllegalArgumentException("soaDetailPerLevel length must equal levels");
         long tot = (long) batchSize * signalLength;
         double[] hs = scaled(wavelet.lowPassDecomposition()), gs = scaled(wavelet.highPassDecomposition());
-        MemorySegment x = VwNative.allocPinned(tot * 8), out = VwNative.allocPinned(tot * 8 * (levels + 1));
+        PinnedArena pin = PinnedArena.current();
+        pin.reset();
+        MemorySegment[] seg = pin.takeAll(tot * 8, tot * 8 * (levels + 1));
+        MemorySegment x = seg[0], out = seg[1];
         try (Arena a = Arena.ofConfined()) {
             VwNative.copyIn(x, soaSignals);
             MemorySegment hseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, hs), gseg = a.allocateFrom(ValueLayout.JAVA_DOUBLE, gs);
@@ -158,8 +163,6 @@ public final class GpuMODWTOptimizer implements MODWTOptimizer, AutoCloseable {
             MemorySegment.copy(out, ValueLayout.JAVA_DOUBLE, (long) levels * tot * 8, soaApproxOut, 0, (int) tot);
         } catch (Throwable t) {
             throw VwNative.rethrow(t);
-        } finally {
-            VwNative.freePinned(x); VwNative.freePinned(out);
         }
     }
 

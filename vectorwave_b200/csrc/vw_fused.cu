@@ -770,7 +770,7 @@ namespace {
 // the tile -- six independent tiles per SM interleave their load / compute / store phases better than three of twice
 // the size (4096 x 4096 J = 4: db4 forward 0.137 -> 0.129 ms, haar inverse 0.124 -> 0.120).
 bool lean_small_tiles(const vw_ctx *ctx, int l, int64_t htot) {
-    return (ctx->opt_lean & 1) && ctx->opt_lean_small && l <= 12 && !(l & 1) && htot * 8 <= 1024;
+    return ctx->plan_lean_ok && (ctx->opt_lean & 1) && ctx->opt_lean_small && l <= 12 && !(l & 1) && htot * 8 <= 1024;
 }
 int launch_threads(const vw_ctx *ctx, int l, bool fwd, int nlev, int64_t htot = -1) {
     if (ctx->opt_threads > 0) return (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_threads, 32), kThreads) & ~31;
@@ -806,7 +806,7 @@ size_t smem_bytes(bool fwd, int64_t tile, int64_t htot, bool use_stage, int64_t 
 // does the planner have to budget for the lean kernels' slack?  (quadrature-mirror pairs are assumed from 16 taps on)
 int64_t lean_slack(const vw_ctx *ctx, int l, int first, int nf) {
     const bool lean = (l <= 12 && !(l & 1) && (ctx->opt_lean & 1)) || ((l == 16 || l == 18 || l == 20) && (ctx->opt_lean & 2));
-    return lean && nf <= 6 ? (int64_t)kR * ((int64_t)1 << (first - 1 + nf - 1)) : 0;
+    return lean && ctx->plan_lean_ok && nf <= 6 ? (int64_t)kR * ((int64_t)1 << (first - 1 + nf - 1)) : 0;
 }
 
 // modelled cycles per owned sample (per SM) of one fused group at tile t; INFINITY when it cannot run
@@ -894,7 +894,7 @@ double group_cost(const vw_ctx *ctx, bool fwd, int l, int first, int nf, int64_t
 
 int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n, std::vector<VwPlanGroup> &out) {
     for (const auto &e : ctx->plan_cache)
-        if (e.forward == forward && e.l == l && e.levels == levels && e.n == n) { out = e.groups; return VW_OK; }
+        if (e.forward == forward && e.lean_ok == ctx->plan_lean_ok && e.l == l && e.levels == levels && e.n == n) { out = e.groups; return VW_OK; }
     out.clear();
     // FP64-bound filters (l >= 24) gain nothing from sharing a launch -- the halo recompute only adds FMAs (measured on coif5)
     const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : 4);
@@ -923,7 +923,7 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
     for (int at = levels; at > 0; at -= pick[at].nlev) out.push_back(pick[at]);
     std::reverse(out.begin(), out.end());   // ascending levels; the inverse walks it backwards
     if (ctx->plan_cache.size() >= 32) ctx->plan_cache.erase(ctx->plan_cache.begin());
-    ctx->plan_cache.push_back({forward, l, levels, n, out});
+    ctx->plan_cache.push_back({forward, ctx->plan_lean_ok, l, levels, n, out});
     return VW_OK;
 }
 
@@ -961,7 +961,7 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
     a.log2d0 = p.first_level - 1; a.mode = p.mode; a.tiles_per_row = (int)tiles_per_row;
     a.use_tma = use_tma; a.use_stage = use_stage; a.lrt = p.l;
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < p.l ? f.h[k] : 0.0; a.f.g[k] = k < p.l ? f.g[k] : 0.0; }
-    if (use_tma && ctx->opt_lean) {   // the common case runs on the issue-lean kernels (vw_lean.cu)
+    if (use_tma && ctx->opt_lean && ctx->plan_lean_ok) {   // the common case runs on the issue-lean kernels (vw_lean.cu)
         const int rcl = vw_lean_forward(ctx, p, a.f, tile, htot, hexact, use_stage, launch_threads(ctx, p.l, true, p.nlevels, htot));
         if (rcl != VW_EUNSUPPORTED) return rcl;
     }
@@ -1040,7 +1040,7 @@ int vw_fused_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt &f) {
         a.f.h[k] = k < p.l ? (rev_h ? f.h[p.l - 1 - k] : f.h[k]) : 0.0;
         a.f.g[k] = k < p.l ? (rev_g ? f.g[p.l - 1 - k] : f.g[k]) : 0.0;
     }
-    if (use_tma && ctx->opt_lean && !aligned_stage) {
+    if (use_tma && ctx->opt_lean && ctx->plan_lean_ok && !aligned_stage) {
         const int rcl = vw_lean_inverse(ctx, p, a.f, tile, htot, launch_threads(ctx, p.l, false, p.nlevels, htot));
         if (rcl != VW_EUNSUPPORTED) return rcl;
     }

@@ -62,7 +62,7 @@ struct vw_ctx {
     int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;
-    struct PlanEntry { bool forward; int l, levels; int64_t n; std::vector<VwPlanGroup> groups; };
+    struct PlanEntry { bool forward, lean_ok; int l, levels; int64_t n; std::vector<VwPlanGroup> groups; };
     mutable std::vector<PlanEntry> plan_cache;   // launch plans by shape (the planner costs 2-35 us); cleared by vw_set_option
     // Scratch is per ctx, not per stream: a call that returned without synchronising (VW_FLAG_NO_SYNC) leaves an event
     // behind, and the next call that takes scratch on a DIFFERENT stream waits on it first (vw_scratch)
@@ -81,8 +81,12 @@ struct vw_ctx {
     struct OccEntry { const void *func; int nthreads; size_t smem; int per_sm; };
     std::vector<OccEntry> occ_cache;   // occupancy queries of the tile kernels (vw_fused.cu: prefetch_distance)
     int64_t opt_lean = 3;    // issue-lean tile kernels (vw_lean.cu): bit 0 = filters up to 12 taps, bit 1 = 16..20-tap quadrature-mirror pairs
+    // set by the cascade drivers for the duration of a call: can this call's tile launches take the lean kernels at all
+    // (not SYMMETRIC, no threshold-on-load, full detail mask)?  The planner budgets shared memory / registers / threads for
+    // the kernels that will really run.
+    bool plan_lean_ok = true;
     int64_t opt_lean_small = 1;   // lean short filters: 128-thread CTAs on ~1024-sample tiles (vw_fused.cu: lean_small_tiles)
-    int64_t opt_l2pf = 1;    // tile kernels prefetch the successor CTA's input tile into L2 (x resident CTAs ahead); 0 = off
+    int64_t opt_l2pf = 3;    // L2 prefetch mask of the tile kernels: 1 = the successor CTA's input tile (V + top W), 2 = a synthesis tile's own lower W levels (sym8 J = 8 inverse 2.08 -> 1.97 ms), 4 = the successor's lower W levels too (slower); 0 = off
     std::recursive_mutex mu;   // every public entry point holds it: calls on one ctx from several host threads serialise
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves

@@ -43,7 +43,7 @@ struct LeanInv {
     const double *w; long long ldw, lsw;
     double *out; long long ldo;
     long long n_in, n_out;
-    int tile, htot, pbuf, nlev, log2d0, mode, tiles_per_row, pf_dist, batch;
+    int tile, htot, pbuf, nlev, log2d0, mode, tiles_per_row, pf_dist, pf_mask, batch;
     int ext[kMaxLev];     // input extent of each level of the group beyond the owned samples: Tt + ext[lev]
     double h[VW_LEAN_MAX_L], g[VW_LEAN_MAX_L];
 };
@@ -211,13 +211,26 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
                    true, &bars[1 + slot], false);
     };
     stage_w(top, top & 1);
-    if (a.pf_dist > 0 && tid == 32) {
-        const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
-        const unsigned fb = lin / (unsigned)a.tiles_per_row;
-        if ((int)fb < a.batch) {
-            const long long fg = (long long)(lin - fb * (unsigned)a.tiles_per_row) * T;
-            prefetch_l2_span(a.v + (long long)fb * a.ldv, fg, T + a.htot, a.n_in);
-            prefetch_l2_span(a.w + (long long)top * a.lsw + (long long)fb * a.ldw, fg, T + a.htot, a.n_in);
+    if (tid == 32) {
+        // L2 prefetches (fire and forget; they put more bytes in flight than the one-level-ahead bulk copies can):
+        // bit 0: V and top-level W tile of the CTA that will inherit this slot; bit 1: this tile's own lower W levels, which
+        // the bulk copies below fetch one level at a time; bit 2: the successor's lower W levels as well
+        if ((a.pf_mask & 2) && top > 0)
+            for (int lev = top - 1; lev >= 0; lev--)
+                prefetch_l2_span(a.w + (long long)lev * a.lsw + b * a.ldw, g0, Tt + a.ext[lev], a.n_in);
+        if (a.pf_dist > 0 && (a.pf_mask & 5)) {
+            const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
+            const unsigned fb = lin / (unsigned)a.tiles_per_row;
+            if ((int)fb < a.batch) {
+                const long long fg = (long long)(lin - fb * (unsigned)a.tiles_per_row) * T;
+                if (a.pf_mask & 1) {
+                    prefetch_l2_span(a.v + (long long)fb * a.ldv, fg, T + a.htot, a.n_in);
+                    prefetch_l2_span(a.w + (long long)top * a.lsw + (long long)fb * a.ldw, fg, T + a.htot, a.n_in);
+                }
+                if (a.pf_mask & 4)
+                    for (int lev = top - 1; lev >= 0; lev--)
+                        prefetch_l2_span(a.w + (long long)lev * a.lsw + (long long)fb * a.ldw, fg, T + a.ext[lev], a.n_in);
+            }
         }
     }
     mbar_wait(&bars[0], 0);
@@ -402,6 +415,7 @@ int vw_lean_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt32 &f, int64_t
     a.n_in = p.n_in; a.n_out = p.n_out; a.batch = (int)p.batch;
     a.tile = (int)tile; a.htot = (int)htot; a.nlev = p.nlevels; a.log2d0 = p.first_level - 1; a.mode = p.mode;
     a.tiles_per_row = (int)tiles_per_row;
+    a.pf_mask = (int)ctx->opt_l2pf;
     const int64_t d0 = 1ll << (p.first_level - 1);
     const int64_t dmax = d0 << (p.nlevels - 1);
     for (int i = 0; i < p.nlevels; i++) {

@@ -210,6 +210,7 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
     const bool exact = flags & VW_FLAG_BITEXACT;
     const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE);
     std::vector<VwPlanGroup> plan;
+    ctx->plan_lean_ok = mode != VW_SYMMETRIC;
     if (allow_fused) vw_plan_levels(ctx, true, l, levels, n, plan);
     else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
     double *buf[2] = {nullptr, nullptr};
@@ -273,6 +274,10 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
             plain = plain && align[j].sigma_h == 1 && align[j].sigma_g == 1 && align[j].tau_h == 0 && align[j].tau_g == 0;
     const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE) && plain && mode != VW_SYMMETRIC;
     std::vector<VwPlanGroup> plan;
+    {
+        const uint64_t full = levels >= 64 ? ~0ull : ((1ull << levels) - 1);
+        ctx->plan_lean_ok = mode != VW_SYMMETRIC && !thr_dev && use_approx && (detail_mask & full) == full;
+    }
     if (allow_fused) vw_plan_levels(ctx, false, l, levels, n, plan);
     else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
     double *buf[2] = {nullptr, nullptr};
@@ -1050,6 +1055,7 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
                           int64_t level_stride_w, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx, "vw_modwt_forward_span");
+    ctx->plan_lean_ok = true;
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
@@ -1120,6 +1126,7 @@ int vw_modwt_stream_level(vw_ctx *ctx, const double *vin, int64_t batch, int64_t
                           double *v, int64_t ldv, uint32_t flags) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx, "vw_modwt_stream_level");
+    ctx->plan_lean_ok = true;
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "streaming calls take device pointers only");
     if (!vin || !w || !v) return vw_fail(ctx, VW_ENULL, "stream buffers cannot be null");
@@ -1158,6 +1165,7 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
                           int32_t nlevels, int32_t order, double *vout, uint32_t flags) {
     if (!ctx) return VW_ENULL;
     DeviceGuard g(ctx, "vw_modwt_inverse_span");
+    ctx->plan_lean_ok = true;
     int rc;
     if (!(flags & VW_FLAG_DEVICE_PTRS)) return vw_fail(ctx, VW_EUNSUPPORTED, "span calls take device pointers only");
     if (!vin || !w || !vout) return vw_fail(ctx, VW_ENULL, "span buffers cannot be null");
