@@ -335,6 +335,126 @@ private:
     std::vector<double> hs_, gs_;
 };
 
+// ---- device-resident result (GpuResidentResult.java): MutableMultiLevelMODWTResult whose coefficients stay in HBM --------
+class ResidentResult {
+public:
+    // MultiLevelMODWTTransform.decomposeMutable (:284-330) with the result kept on the device
+    ResidentResult(const MultiLevelMODWTTransform &t, const std::vector<double> &signal, int levels) : t_(t), n_((int64_t)signal.size()), levels_(levels) {
+        if (signal.empty()) throw InvalidSignalException("Signal cannot be empty for multi-level MODWT", "VAL_006");
+        if (levels < 1 || levels > t.getMaximumLevels((int)signal.size()))
+            throw InvalidArgumentException("Invalid number of decomposition levels: " + std::to_string(levels), "CFG_004");
+        Engine &e = Engine::get();
+        e.check(vw_modwt_decompose_h(e.ctx(), signal.data(), 1, n_, n_, t.scaledLow().data(), t.scaledHigh().data(), (int)t.scaledLow().size(),
+                                     levels, (int)t.getBoundaryMode(), &res_, VW_FLAG_CHECK_FINITE));
+    }
+    ~ResidentResult() { if (res_) vw_result_free(Engine::get().ctx(), res_); }
+    ResidentResult(const ResidentResult &) = delete;
+    ResidentResult &operator=(const ResidentResult &) = delete;
+    int getLevels() const { return levels_; }
+    std::vector<double> getDetailCoeffsAtLevel(int level) const { return fetch(level, 1); }
+    std::vector<double> getApproximationCoeffs() const { return fetch(0, 0); }
+    void applyThreshold(int level, double threshold, bool soft) {   // MutableMultiLevelMODWTResult.applyThreshold (:83-118)
+        Engine &e = Engine::get();
+        e.check(vw_result_threshold(e.ctx(), res_, level, &threshold, 0, soft ? 1 : 0));
+    }
+    double applyUniversalThreshold(bool soft) {                     // VectorWaveSwtAdapter.applyUniversalThreshold (:505-520)
+        double thr = 0.0;
+        Engine &e = Engine::get();
+        e.check(vw_result_universal_threshold(e.ctx(), res_, soft ? 1 : 0, &thr));
+        return thr;
+    }
+    double getDetailEnergyAtLevel(int level) const { double v = 0; Engine &e = Engine::get(); e.check(vw_result_energy(e.ctx(), res_, level, &v)); return v; }
+    std::vector<double> reconstruct() const {                       // MultiLevelMODWTTransform.reconstruct (:339-349)
+        int order;
+        const std::vector<vw_align> al = t_.alignment(levels_, order);
+        std::vector<double> x((size_t)n_);
+        Engine &e = Engine::get();
+        e.check(vw_modwt_reconstruct_h(e.ctx(), res_, t_.scaledLow().data(), t_.scaledHigh().data(), (int)t_.scaledLow().size(),
+                                       (int)t_.getBoundaryMode(), al.empty() ? nullptr : al.data(), order, (1ull << levels_) - 1, 1,
+                                       x.data(), n_, 0));
+        return x;
+    }
+
+private:
+    std::vector<double> fetch(int level, int lo) const {
+        if (level < lo || level > levels_) throw IllegalArgumentException("Level must be between 1 and " + std::to_string(levels_));
+        std::vector<double> out((size_t)n_);
+        Engine &e = Engine::get();
+        e.check(vw_result_get_level(e.ctx(), res_, level, out.data(), n_, 0));
+        return out;
+    }
+    const MultiLevelMODWTTransform &t_;
+    int64_t n_;
+    int levels_;
+    vw_result *res_ = nullptr;
+};
+
+// ---- one long signal over several GPUs, driven by one host thread (vw_init_multi) ---------------
+class ShardedMODWT {
+public:
+    // devices: one entry per span (a device may be listed more than once); PERIODIC or ZERO_PADDING
+    ShardedMODWT(const Wavelet &w, BoundaryMode m, int levels, int64_t n_local, const std::vector<int> &devices)
+        : mode_(m), levels_(levels), n_(n_local), hs_(detail::scaled(w.lowPassDecomposition())), gs_(detail::scaled(w.highPassDecomposition())) {
+        int rc = vw_span_plan_query((int)hs_.size(), levels, n_local, (int)devices.size(), &plan_);
+        if (rc != VW_OK) throw IllegalArgumentException(std::string("vw_span_plan_query: ") + vw_status_name(rc));
+        rc = vw_init_multi(devices.data(), (int)devices.size(), &m_);
+        if (rc != VW_OK) throw NativeEngineError(std::string("vw_init_multi failed: ") + vw_status_name(rc));
+        row_ = plan_.lead_w + n_ + plan_.pad;
+        for (size_t r = 0; r < devices.size(); r++) {
+            void *x, *wv, *v, *o;
+            vw_ctx *c = vw_multi_ctx(m_, (int)r);
+            if (vw_device_alloc(c, (size_t)(plan_.lead + n_) * 8, &x) || vw_device_alloc(c, (size_t)levels * row_ * 8, &wv) ||
+                vw_device_alloc(c, (size_t)(n_ + plan_.pad) * 8, &v) || vw_device_alloc(c, (size_t)n_ * 8, &o))
+                throw NativeEngineError("device allocation failed");
+            xext_.push_back((double *)x); w_.push_back((double *)wv); v_.push_back((double *)v); out_.push_back((double *)o);
+        }
+    }
+    ~ShardedMODWT() {
+        for (size_t r = 0; r < xext_.size(); r++) {
+            vw_ctx *c = vw_multi_ctx(m_, (int)r);
+            vw_device_free(c, xext_[r]); vw_device_free(c, w_[r]); vw_device_free(c, v_[r]); vw_device_free(c, out_[r]);
+        }
+        if (m_) vw_destroy_multi(m_);
+    }
+    ShardedMODWT(const ShardedMODWT &) = delete;
+    ShardedMODWT &operator=(const ShardedMODWT &) = delete;
+    // signal: world * n_local samples on the host; details come back as [levels][world * n_local], approximation [world * n_local]
+    void decompose(const std::vector<double> &signal, std::vector<double> &details, std::vector<double> &approx) {
+        const size_t world = xext_.size(), total = world * (size_t)n_;
+        if (signal.size() != total) throw IllegalArgumentException("signal length must be world * n_local");
+        for (size_t r = 0; r < world; r++)
+            chk(r, vw_copy_h2d(vw_multi_ctx(m_, (int)r), xext_[r] + plan_.lead, signal.data() + r * n_, (size_t)n_ * 8));
+        mchk(vw_modwt_forward_sharded(m_, &plan_, xext_.data(), hs_.data(), gs_.data(), (int)mode_, w_.data(), row_, v_.data(), nullptr, 0));
+        details.resize((size_t)levels_ * total); approx.resize(total);
+        for (size_t r = 0; r < world; r++) {
+            vw_ctx *c = vw_multi_ctx(m_, (int)r);
+            for (int j = 0; j < levels_; j++)
+                chk(r, vw_copy_d2h(c, details.data() + (size_t)j * total + r * n_, w_[r] + (size_t)j * row_ + plan_.lead_w, (size_t)n_ * 8));
+            chk(r, vw_copy_d2h(c, approx.data() + r * n_, v_[r], (size_t)n_ * 8));
+        }
+    }
+    // reconstruct from the coefficients the last decompose left on the devices
+    std::vector<double> reconstruct() {
+        const size_t world = xext_.size();
+        mchk(vw_modwt_inverse_sharded(m_, &plan_, w_.data(), row_, v_.data(), hs_.data(), gs_.data(), (int)mode_,
+                                      mode_ == BoundaryMode::ZERO_PADDING ? VW_ORDER_PAIR : VW_ORDER_SPLIT, out_.data(), nullptr, 0));
+        std::vector<double> x(world * (size_t)n_);
+        for (size_t r = 0; r < world; r++) chk(r, vw_copy_d2h(vw_multi_ctx(m_, (int)r), x.data() + r * n_, out_[r], (size_t)n_ * 8));
+        return x;
+    }
+
+private:
+    void mchk(int rc) const { if (rc != VW_OK) throw NativeEngineError(vw_multi_last_error(m_)); }
+    void chk(size_t r, int rc) const { if (rc != VW_OK) throw NativeEngineError(vw_last_error(vw_multi_ctx(m_, (int)r))); }
+    BoundaryMode mode_;
+    int levels_;
+    int64_t n_, row_ = 0;
+    std::vector<double> hs_, gs_;
+    vw_span_plan plan_{};
+    vw_multi *m_ = nullptr;
+    std::vector<double *> xext_, w_, v_, out_;
+};
+
 // ---- VectorWaveSwtAdapter ---------------------------------------------------------------------------------------------
 class VectorWaveSwtAdapter {
 public:

@@ -108,6 +108,47 @@ int main() {
         expect_close(a1, v1.data(), 1e-12 * 6.0, "SoA haar V");
         expect_close(d1, w1.data(), 1e-12 * 6.0, "SoA haar W");
     }
+    // device-resident result: levels on request, universal threshold where the coefficients are, reconstruct
+    {
+        const int n = 5000, levels = 4;
+        std::vector<double> x(n), xr(n), wo((size_t)levels * n), vo(n);
+        double xmax = 0;
+        for (double &v : x) { v = nd(rng); xmax = std::fmax(xmax, std::fabs(v)); }
+        const Wavelet w8 = wavelets::db8();
+        const std::vector<double> h = w8.lowPassDecomposition(), g = w8.highPassDecomposition();
+        for (BoundaryMode m : modes) {
+            MultiLevelMODWTTransform mt(w8, m);
+            ResidentResult rr(mt, x, levels);
+            vwo_decompose(x.data(), n, h.data(), g.data(), (int64_t)h.size(), levels, (int)m, 0, wo.data(), vo.data());
+            for (int j = 1; j <= levels; j++) expect_close(rr.getDetailCoeffsAtLevel(j), wo.data() + (size_t)(j - 1) * n, 1e-12 * xmax, "resident W_j");
+            expect_close(rr.getApproximationCoeffs(), vo.data(), 1e-12 * xmax, "resident V_J");
+            vwo_reconstruct(wo.data(), vo.data(), n, h.data(), g.data(), (int64_t)h.size(), levels, (int)m, 2, 0, (1ull << levels) - 1, 1, xr.data());
+            expect_close(rr.reconstruct(), xr.data(), 1e-12 * xmax, "resident reconstruct");
+            const double thr = rr.applyUniversalThreshold(true);
+            const double tref = vwo_swt_denoise(x.data(), n, h.data(), g.data(), (int64_t)h.size(), levels, (int)m, 2, -1.0, 1, 0, xr.data());
+            if (!(std::fabs(thr - tref) <= 1e-12 * tref)) { std::printf("FAIL resident universal threshold %.17g vs %.17g\n", thr, tref); failures++; }
+            expect_close(rr.reconstruct(), xr.data(), 1e-12 * xmax, "resident denoise");
+        }
+    }
+    // one long signal over three spans (all on device 0 here) driven from this one thread: equals the unsharded transform
+    {
+        const int world = 3, levels = 6;
+        const int64_t nl = 1 << 14, n = world * nl;
+        std::vector<double> x((size_t)n), xr((size_t)n), wo((size_t)levels * n), vo((size_t)n), det, app;
+        double xmax = 0;
+        for (double &v : x) { v = nd(rng); xmax = std::fmax(xmax, std::fabs(v)); }
+        const Wavelet w4 = wavelets::db4();
+        const std::vector<double> h = w4.lowPassDecomposition(), g = w4.highPassDecomposition();
+        for (BoundaryMode m : {BoundaryMode::PERIODIC, BoundaryMode::ZERO_PADDING}) {
+            ShardedMODWT sh(w4, m, levels, nl, std::vector<int>(world, 0));
+            sh.decompose(x, det, app);
+            vwo_decompose(x.data(), n, h.data(), g.data(), (int64_t)h.size(), levels, (int)m, 0, wo.data(), vo.data());
+            expect_close(det, wo.data(), 1e-12 * xmax, "sharded W");
+            expect_close(app, vo.data(), 1e-12 * xmax, "sharded V_J");
+            vwo_reconstruct(wo.data(), vo.data(), n, h.data(), g.data(), (int64_t)h.size(), levels, (int)m, 0, 0, (1ull << levels) - 1, 1, xr.data());
+            expect_close(sh.reconstruct(), xr.data(), 1e-12 * xmax, "sharded reconstruct");
+        }
+    }
     if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
     std::printf("ok\n");
     return 0;

@@ -48,6 +48,20 @@ int main(int argc, char **argv) {
     for (int i = 0; i < reps; i++) CK(vw_graph_launch(ctx, g1, 0));
     const double c1_graph = (now_us() - t0) / reps;
     const double w_check = w[17];
+    // the same call with the pinned buffers addressed in place by the kernels (vw_set_option "zero_copy"): run with a third
+    // argument "zc"; results must be identical to the staged call's
+    double c1_zc = -1.0, zc_diff = -1.0;
+    if (argc > 3) {
+        std::vector<double> wref(w, w + n), vref(v, v + n);
+        CK(vw_set_option(ctx, "zero_copy", 1 << 20));
+        for (int i = 0; i < 20; i++) CK(vw_modwt_forward(ctx, x, 1, n, n, hs, gs, 8, 1, VW_PERIODIC, w, n, n, v, n, 0));
+        t0 = now_us();
+        for (int i = 0; i < reps; i++) CK(vw_modwt_forward(ctx, x, 1, n, n, hs, gs, 8, 1, VW_PERIODIC, w, n, n, v, n, 0));
+        c1_zc = (now_us() - t0) / reps;
+        zc_diff = 0.0;
+        for (int64_t i = 0; i < n; i++) zc_diff = fmax(zc_diff, fmax(fabs(w[i] - wref[i]), fabs(v[i] - vref[i])));
+        CK(vw_set_option(ctx, "zero_copy", 0));
+    }
 
     // ---- c2s: 16 x 4096, J = 4, device-resident -------------------------------------------------------------
     const int64_t b = 16, levels = 4;
@@ -86,8 +100,9 @@ int main(int argc, char **argv) {
     printf("{\"reps\": %d, \"c1_1x4096_db4_J1_forward_host_buffers_us\": %.2f, \"c1_graph_replay_us\": %.2f, "
            "\"c2s_16x4096_db4_J4_forward_device_sync_us\": %.2f, \"c2s_no_sync_back_to_back_us\": %.2f, "
            "\"c2s_graph_replay_back_to_back_us\": %.2f, \"c2s_graph_replay_sync_us\": %.2f, \"check\": %.17g, "
+           "\"c1_zero_copy_us\": %.2f, \"c1_zero_copy_max_abs_diff\": %g, "
            "\"reference_jvm_us\": {\"core\": 358, \"extensions\": 117, \"source\": \"docs/BENCHMARK-RESULTS.md:26\"}}\n",
-           reps, c1_call, c1_graph, c2_sync, c2_nosync, c2_graph, c2_graph_sync, w_check);
+           reps, c1_call, c1_graph, c2_sync, c2_nosync, c2_graph, c2_graph_sync, w_check, c1_zc, zc_diff);
     vw_graph_destroy(ctx, g1);
     vw_graph_destroy(ctx, g2);
     vw_device_free(ctx, xd); vw_device_free(ctx, wd); vw_device_free(ctx, vd);

@@ -27,10 +27,13 @@ x = torch.randn((a.batch, n), dtype=torch.float64, device="cuda")
 w = torch.empty((a.levels, a.batch, n), dtype=torch.float64, device="cuda")
 v = torch.empty((a.batch, n), dtype=torch.float64, device="cuda")
 xr = torch.empty((a.batch, n), dtype=torch.float64, device="cuda")
+from vectorwave_b200.modwt import multilevel_alignment  # noqa: E402
+bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][a.mode]
+align, order = multilevel_alignment(wv, bm, a.levels)
 for _ in range(a.warm + 1):
     eng.forward(x, hs, gs, a.levels, a.mode, 0, w, v)
-    eng.inverse(w, v, hs, gs, a.mode, None, 1 if a.mode == 1 else 0, out=xr)
+    eng.inverse(w, v, hs, gs, a.mode, align, order, out=xr)
     if a.denoise:
-        eng.denoise(x, hs, gs, a.levels, a.mode, None, 1 if a.mode == 1 else 0, -1.0, True)
+        eng.denoise(x, hs, gs, a.levels, a.mode, align, order, -1.0, True)
 torch.cuda.synchronize()
 print("rt_err", float((xr - x).abs().max()))

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
-    stage_tile(lean_smem, a.x + b * a.ldx, g0 - HT, PP, a.n_in, a.mode, true, bar, false);
+    // PERIODIC rows are staged by thread 0 alone (bulk copies only): the other warps skip the address arithmetic
+    if (a.mode != VW_PERIODIC || tid == 0) stage_tile(lean_smem, a.x + b * a.ldx, g0 - HT, PP, a.n_in, a.mode, true, bar, false);
     if (a.pf_dist > 0 && tid == 32) {
         // the CTA that will inherit this slot: its input tile goes to L2 now (see vw_fused.cu)
         const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
@@ -205,10 +206,12 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
     __syncthreads();
     const int top = a.nlev - 1;
     // bulk copies move 16-byte units: extents are even by construction (Tt even, ext even)
-    stage_tile(lean_smem, a.v + b * a.ldv, g0, Tt + a.ext[top], a.n_in, a.mode, true, &bars[0], false);
+    const bool stager = a.mode != VW_PERIODIC || tid == 0;   // PERIODIC: thread 0 alone issues the bulk copies
+    if (stager) stage_tile(lean_smem, a.v + b * a.ldv, g0, Tt + a.ext[top], a.n_in, a.mode, true, &bars[0], false);
     auto stage_w = [&](int lev, int slot) {
-        stage_tile(lean_smem + (2 + slot) * PB, a.w + (long long)lev * a.lsw + b * a.ldw, g0, Tt + a.ext[lev], a.n_in, a.mode,
-                   true, &bars[1 + slot], false);
+        if (stager)
+            stage_tile(lean_smem + (2 + slot) * PB, a.w + (long long)lev * a.lsw + b * a.ldw, g0, Tt + a.ext[lev], a.n_in, a.mode,
+                       true, &bars[1 + slot], false);
     };
     stage_w(top, top & 1);
     if (tid == 32) {
