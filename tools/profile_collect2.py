@@ -43,17 +43,17 @@ if os.path.exists(lp):
         a[0] += 1
         a[1] += d.get("gpu__time_duration.sum", 0.0)
     total = sum(v[1] for v in agg.values())
-    ours = sum(v[1] for k, v in agg.items() if k.startswith("k_"))
+    ours = sum(v[1] for k, v in agg.items() if k.startswith("k_") and "probe" not in k)
     with open(os.path.join(P, f"{R}_launches_bench.md"), "w") as f:
         f.write(f"# ncu launch list, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra` ({R})\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none` -- per-launch times are cold-cache and serialised; what must "
                 "agree with bench.py is each kernel's SHARE of the engine's launches.\n\n"
                 "| kernel | launches | total us | avg us | share of all GPU time | share of engine kernels |\n|---|---|---|---|---|---|\n")
         for k, (c, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            sh2 = f"{100 * ns / ours:.1f} %" if k.startswith("k_") and ours else "-"
+            sh2 = f"{100 * ns / ours:.1f} %" if k.startswith("k_") and "probe" not in k and ours else "-"
             f.write(f"| `{k[:90]}` | {c} | {ns / 1e3:.1f} | {ns / c / 1e3:.1f} | {100 * ns / total:.1f} % | {sh2} |\n")
         f.write("\n(torch kernels are the synthetic-input generator and the round-trip check outside the timed region; "
-                "k_probe_dfma is the FP64 roof measurement.)\n")
+                "k_probe_dfma is the FP64 roof measurement bench.py makes once per run, outside the timed region: not an engine kernel.)\n")
     with open(os.path.join(P, f"{R}_launches_bench.csv"), "w") as f:
         f.write("kernel,grid,block,duration_ns\n")
         for d in launches:

@@ -897,7 +897,9 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
         if (e.forward == forward && e.lean_ok == ctx->plan_lean_ok && e.l == l && e.levels == levels && e.n == n) { out = e.groups; return VW_OK; }
     out.clear();
     // FP64-bound filters (l >= 24) gain nothing from sharing a launch -- the halo recompute only adds FMAs (measured on coif5)
-    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : 4);
+    // 16-20 taps are FP64-pipe bound in the analysis: two levels per launch keep the halo recompute small (sym8 J = 8 forward
+    // 1.62 -> 1.57 ms, db8 J = 6 4.58 -> 4.39); the synthesis, which re-reads a W halo per level either way, prefers four
+    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : (l >= 16 && forward ? 2 : 4));
     const double kGeneric = 60.0;  // per-level kernels: one thread per output through L1/L2
     std::vector<double> best(levels + 1, INFINITY);
     std::vector<VwPlanGroup> pick(levels + 1);
