@@ -37,9 +37,6 @@ namespace {
 #ifndef VW_FENCE_MIN
 #define VW_FENCE_MIN 0
 #endif
-#ifndef VW_WAVEFRONT
-#define VW_WAVEFRONT 0   // 1 (developer builds, untested on hardware): see the wavefront block in k_fused_analysis
-#endif
 #ifndef VW_EXP_NOSTORE
 #define VW_EXP_NOSTORE 0   // 1 (developer builds, WRONG results): the analysis tile kernel skips its global stores -- compute-only timing
 #endif
@@ -254,9 +251,6 @@ struct FwdArgs {
     long long n_in, t0, n_out, batch;
     int tile, htot, slack, nlev, log2d0, mode, tiles_per_row, use_tma, use_stage, lrt;
     int pf_dist;   // > 0: prefetch into L2 the input tile of the CTA `pf_dist` launches ahead (the one that takes this CTA's slot)
-#if VW_WAVEFRONT
-    int wavefront; // levels synchronise warp to warp (progress flags) instead of through CTA barriers
-#endif
     VwFilt32 f;
 };
 
@@ -316,79 +310,9 @@ __global__ void __launch_bounds__(kThreads, (L > 0 && L <= VW_LB4_MAXL) ? 4 : ((
         }
     }
     if (a.use_tma) mbar_wait(bar, 0);
-#if VW_WAVEFRONT
-    if (tid < 8) reinterpret_cast<volatile int *>(bar + 1)[tid] = 0;   // per-warp count of finished levels (inside the 64-byte barrier slot)
-#endif
     __syncthreads();
     VW_PHASE(1);
 
-#if VW_WAVEFRONT
-    // EXPERIMENTAL, queued for an A/B on hardware.  One item per thread per level (host guarantees
-    // it), dilation <= 32: warp w owns the 288 contiguous samples [ra + 288 w, ra + 288 (w + 1)) of every level.  A level-
-    // (j+1) item reads level-j outputs of its own warp and of warp w+1 (ranges shift right by the level's halo), and it
-    // overwrites level-(j-1) values that warps w+1 and w+2 may still be reading for level j -- so a warp may start level
-    // j+1 once warps w+1 and w+2 have published level j.  Dependencies only point right: no cycle, the last warp runs free.
-    if (kMergedHalo && a.wavefront) {
-        constexpr int LL = L > 0 ? L : 2;
-        const int w = tid >> 5, lane = tid & 31, nw = (int)blockDim.x >> 5;
-        volatile int *prog = reinterpret_cast<volatile int *>(bar + 1);
-        double *cur = buf0, *nxt = buf1;
-        int lo = a.slack;
-        for (int lev = 0; lev < a.nlev; lev++) {
-            const int ld2 = a.log2d0 + lev, d = 1 << ld2;
-            const bool last = lev + 1 == a.nlev;
-            lo += (LR - 1) << ld2;                              // first index where V_lev is defined
-            const bool staged = a.use_stage && d < 4;
-            double *stg = (lev & 1) ? stg1 : stg0;
-            double *wrow = a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0);
-            const int ra = last ? HT : lo, rb = PP;
-            if (lev > 0) {
-                if (lane == 0) {
-                    if (w + 1 < nw) while (prog[w + 1] < lev) {}
-                    if (w + 2 < nw) while (prog[w + 2] < lev) {}
-                }
-                __syncwarp();
-                __threadfence_block();
-            }
-            const int qh = (HT - ra) >> ld2;
-            const int c = tid >> ld2, ph = tid & (d - 1);
-            const int base = ra + ((c * kR) << ld2) + ph;
-            if (base < rb) {
-                const int nvalid = min(kR, (rb - base + d - 1) >> ld2);
-                const bool full = nvalid == kR;
-                const int rlo = qh - c * kR;
-                const double *top = cur + base + ((kR - 1) << ld2);
-                double ah[kR], ag[kR];
-                if (full) analysis_item<LL, kR, true, true, QMF>(top, d, nvalid, a.f, ah, ag);
-                else analysis_item<LL, kR, true, false, QMF>(top, d, nvalid, a.f, ah, ag);
-                double *q = nxt + base;
-                double *wq = (staged ? stg : wrow) + (base - HT);
-#pragma unroll
-                for (int r = 0; r < kR; r++) {
-                    if (full || r < nvalid) { *q = ah[r]; if (r >= rlo) *wq = ag[r]; }
-                    q += d; wq += d;
-                }
-            }
-            // publish this warp's segment; its owned part leaves through the warp's own bulk stores
-            const int s0 = max(ra + w * 32 * kR, HT), s1 = min(ra + (w + 1) * 32 * kR, rb);
-            if (staged || last) fence_async_smem();
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                if (s1 > s0) {
-                    if (staged) { bulk_s2g(wrow + (s0 - HT), stg + (s0 - HT), (uint32_t)(s1 - s0) * 8u); bulk_commit(); }
-                    if (last) { bulk_s2g(a.v + b * a.ldv + (g0 - a.t0) + (s0 - HT), nxt + s0, (uint32_t)(s1 - s0) * 8u); bulk_commit(); }
-                }
-                prog[w] = lev + 1;
-            }
-            double *t = cur; cur = nxt; nxt = t;
-            if (lev < 4) VW_PHASE(2 + lev);
-        }
-        if (lane == 0) bulk_wait_read<0>();
-        VW_PHASE(7);
-        return;
-    }
-#endif
 
     double *cur = buf0, *nxt = buf1;
     int lo_prev = 0;
@@ -967,20 +891,6 @@ int vw_fused_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt &f) {
         const int rcl = vw_lean_forward(ctx, p, a.f, tile, htot, hexact, use_stage, launch_threads(ctx, p.l, true, p.nlevels, htot));
         if (rcl != VW_EUNSUPPORTED) return rcl;
     }
-#if VW_WAVEFRONT
-    {   // one item per thread at every level, dilation <= 32, bulk path, no per-level mirror patch
-        bool ok = use_tma && p.mode != VW_SYMMETRIC && p.l <= VW_MERGED_MAXL && p.first_level + p.nlevels - 1 <= 6;
-        int64_t lo = htot - hexact;
-        for (int i = 0; ok && i < p.nlevels; i++) {
-            const int64_t d = d0 << i;
-            lo += (int64_t)(p.l - 1) * d;
-            const int64_t ra = i + 1 == p.nlevels ? htot : lo;
-            const int64_t items = ceil_div(ceil_div(htot + tile - ra, d), kR) * d;
-            ok = items <= launch_threads(ctx, p.l, true, p.nlevels, htot);
-        }
-        a.wavefront = ok;
-    }
-#endif
     const size_t smem = smem_for(tile);
     const unsigned grid = (unsigned)(tiles_per_row * p.batch);
     const int nthreads = launch_threads(ctx, p.l, true, p.nlevels, htot);
