@@ -729,6 +729,19 @@ def main():
             extra["batch_strong_c3"]["scaling"] = "strong"
             extra["batch_strong_c3"]["sharding"] = f"1024 signals split by signal over {world} ranks, no communication"
         guarded("span", lambda: extra_span(c))
+        if world > 1:
+            # what the box's PCIe fabric gives when every rank copies at once (e2e at N > 1 is bound by this, not by the engine)
+            c.barrier()
+            mine = dict(pcie_probe(c), rank=rank, numa_binding=numa)
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+            if rank == 0:
+                extra["pcie_all_ranks_concurrently"] = {
+                    "h2d_gbs_min": min(p["h2d_gbs"] for p in allp), "h2d_gbs_max": max(p["h2d_gbs"] for p in allp),
+                    "d2h_gbs_min": min(p["d2h_gbs"] for p in allp), "d2h_gbs_max": max(p["d2h_gbs"] for p in allp),
+                    "h2d_gbs_sum": sum(p["h2d_gbs"] for p in allp), "d2h_gbs_sum": sum(p["d2h_gbs"] for p in allp),
+                    "numa_bindings": [p["numa_binding"] for p in allp],
+                    "note": "1 GiB pinned copies issued by all ranks at the same time, one direction after the other"}
         if world == 1:
             guarded("pcie", lambda: pcie_probe(c))
             guarded("c4", lambda: finish_batch(c, "single2p28_coif5_J10",
