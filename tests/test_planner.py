@@ -50,3 +50,37 @@ def test_forced_tile_and_fuse_are_honoured():
     rows = re.findall(r"levels (\d+)-(\d+): (\w+) tile=(-?\d+)", text)
     assert all(int(b) - int(a) + 1 <= 2 for a, b, _, _ in rows)
     assert all(int(t) == 1024 for _, _, k, t in rows if k == "fused")
+
+
+@pytest.mark.parametrize("l,levels,n_local,world", [(30, 10, 1 << 25, 8), (30, 10, 1 << 28, 1), (8, 6, 1 << 16, 2),
+                                                    (16, 7, 1 << 16, 1), (2, 9, 1 << 13, 3), (8, 5, 1 << 14, 4)])
+def test_span_plan_layout_invariants(l, levels, n_local, world):
+    """vw_span_plan_query (host logic only): groups tile 1..J in both directions and equal the planner's groups for the
+    WHOLE signal, every halo covers its group and is a multiple of 32 samples, lead / lead_w / pad / inverse_msg are the
+    sums the cascades and the message packing rely on."""
+    p = _native.span_plan(l, levels, n_local, world)
+    gf = [(p.first_f[g], p.nlev_f[g]) for g in range(p.ngroups_f)]
+    gi = [(p.first_i[g], p.nlev_i[g]) for g in range(p.ngroups_i)]
+    assert gf == _native.plan_groups(1, l, levels, n_local * world)
+    assert gi == _native.plan_groups(0, l, levels, n_local * world)
+    for groups, halos in ((gf, p.halo_f), (gi, p.halo_i)):
+        nxt = 1
+        for g, (first, nlev) in enumerate(groups):
+            assert first == nxt
+            nxt = first + nlev
+            need = (l - 1) * (1 << (first - 1)) * ((1 << nlev) - 1)
+            assert halos[g] >= need and halos[g] % 32 == 0 and halos[g] - need < 32
+        assert nxt == levels + 1
+    assert p.lead == sum(p.halo_f[:p.ngroups_f]) and p.lead_w == sum(p.halo_f[1:p.ngroups_f])
+    assert p.pad == sum(p.halo_i[:p.ngroups_i])
+    si_in = [sum(p.halo_i[:g + 1]) for g in range(p.ngroups_i)]
+    assert p.inverse_msg == si_in[-1] + sum(n * s for (_, n), s in zip(gi, si_in))
+    assert max(p.lead, p.pad) <= n_local and (p.l, p.levels, p.world, p.n_local) == (l, levels, world, n_local)
+
+
+def test_span_plan_rejects_what_cannot_be_sharded():
+    from vectorwave_b200.errors import IllegalArgumentException, InvalidArgumentException
+    with pytest.raises(IllegalArgumentException):       # total halo 29 * 255 > 256 samples per rank
+        _native.span_plan(30, 8, 256, 64)
+    with pytest.raises(InvalidArgumentException):       # upsampled filter longer than the whole signal
+        _native.span_plan(30, 8, 256, 4)
