@@ -467,3 +467,22 @@ def test_seeded_random_shapes_against_the_oracle(eng):
             ref = cref.reconstruct(w[:, i, :], v[i], h, g, mode, wid)
             assert float(np.max(np.abs(xr[i] - ref))) <= t * 4, ctx
         done += 1
+
+
+def test_batches_larger_than_one_grid_dimension(eng):
+    """40000 rows: the lean tile kernels spread the batch over grid.y x grid.z; rows on both sides of the seam, forward and
+    inverse, against the oracle."""
+    import torch
+    h, g, wid = filters("db2")
+    hs, gs = h * S, g * S
+    b, n, levels = 40000, 256, 3
+    x = _device_signal(b, n, 5)
+    w, v = eng.forward(x, hs, gs, levels, 0)
+    xr = eng.inverse(w, v, hs, gs, 0)
+    torch.cuda.synchronize()
+    for i in (0, 1, 32767, 32768, 32769, b - 1):
+        row = x[i].cpu().numpy()
+        wo, vo = cref.decompose(row, h, g, levels, 0)
+        np.testing.assert_allclose(w[:, i].cpu().numpy(), wo, rtol=0, atol=tol(row))
+        np.testing.assert_allclose(v[i].cpu().numpy(), vo, rtol=0, atol=tol(row))
+        np.testing.assert_allclose(xr[i].cpu().numpy(), cref.reconstruct(wo, vo, h, g, 0, wid), rtol=0, atol=tol(row))

@@ -40,14 +40,16 @@ def run(name, reps, opts, mode=0, denoise=False):
     vs = [torch.empty((b, n), dtype=torch.float64, device="cuda") for _ in range(nsets)]
     xrs = [torch.empty((b, n), dtype=torch.float64, device="cuda") for _ in range(nsets)]
     x, w, v, xr = xs[0], ws[0], vs[0], xrs[0]
-    order = 1 if mode == 1 else 0
+    from vectorwave_b200.modwt import multilevel_alignment
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(wv, bm, levels)
     it = [0]
     def fwd():
         k = it[0] % nsets; it[0] += 1
         eng.forward(xs[k], hs, gs, levels, mode, 0, ws[k], vs[k])
     def inv():
         k = it[0] % nsets; it[0] += 1
-        eng.inverse(ws[k], vs[k], hs, gs, mode, None, order, out=xrs[k])
+        eng.inverse(ws[k], vs[k], hs, gs, mode, align, order, out=xrs[k])
     for k in range(nsets):
         eng.forward(xs[k], hs, gs, levels, mode, 0, ws[k], vs[k])
     out = {"config": name, "opts": opts, "mode": mode}
@@ -70,7 +72,7 @@ def run(name, reps, opts, mode=0, denoise=False):
     if denoise:
         y = torch.empty_like(x)
         def den():
-            eng.denoise(x, hs, gs, levels, mode, None, order, -1.0, True)
+            eng.denoise(x, hs, gs, levels, mode, align, order, -1.0, True)
         for _ in range(2):
             den()
         torch.cuda.synchronize()

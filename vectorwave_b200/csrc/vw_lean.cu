@@ -44,6 +44,7 @@ struct LeanInv {
     double *out; long long ldo;
     long long n_in, n_out;
     int tile, htot, pbuf, nlev, log2d0, mode, tiles_per_row, pf_dist, pf_mask, batch;
+    const double *thr; int thr_per_row, thr_soft;   // SWT denoise: threshold every W tile as it lands (nullptr: off)
     int ext[kMaxLev];     // input extent of each level of the group beyond the owned samples: Tt + ext[lev]
     double h[VW_LEAN_MAX_L], g[VW_LEAN_MAX_L];
 };
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
     uint64_t *bar = reinterpret_cast<uint64_t *>(lean_smem + 2 * PB + (a.use_stage ? 2 * T : 0));
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
-    const long long b = blockIdx.y;
+    const long long b = blockIdx.y + (long long)blockIdx.z * gridDim.y;   // batches beyond 32768 rows spill into grid.z
+    if (b >= a.batch) return;
     const long long g0 = a.t0 + (long long)tile * T;            // first owned position (input coordinates)
     const long long rem = a.t0 + a.n_out - g0;
     const int Tt = (int)(rem < T ? rem : T);                     // owned samples of this tile
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
     if (a.mode != VW_PERIODIC || tid == 0) stage_tile(lean_smem, a.x + b * a.ldx, g0 - HT, PP, a.n_in, a.mode, true, bar, false);
     if (a.pf_dist > 0 && tid == 32) {
         // the CTA that will inherit this slot: its input tile goes to L2 now (see vw_fused.cu)
-        const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
+        const unsigned lin = (unsigned)b * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
         const unsigned fb = lin / (unsigned)a.tiles_per_row;
         if ((int)fb < a.batch) {
             const unsigned ft = lin - fb * (unsigned)a.tiles_per_row;
@@ -175,6 +177,14 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_analysis(const __
             bulk_s2g(a.w + (long long)lev * a.lsw + b * a.ldw + (g0 - a.t0), lean_smem + ((ostg8 - sbase) >> 3), (uint32_t)Tt * 8u);
             bulk_commit();
         }
+        // SYMMETRIC: V_lev at positions < 0 is the mirror of V_lev itself (ScalarOps.java:818-835 applied per level); only
+        // the first tile(s) of a row hold such positions
+        if (a.mode == VW_SYMMETRIC && lev + 1 < a.nlev && g0 - HT < 0) {
+            const int neg = (int)(HT - g0);                     // tile indices [0, neg) are positions < 0
+            double *vn = lean_smem + ((nxt8 - sbase) >> 3);
+            for (int i = ra + tid; i < neg; i += (int)blockDim.x) vn[i] = vn[2 * neg - 1 - i];   // position p -> -1 - p
+            __syncthreads();
+        }
         const uint32_t t = cur8; cur8 = nxt8; nxt8 = t;
     }
     if (tid == 0) {
@@ -194,7 +204,8 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
     uint64_t *bars = reinterpret_cast<uint64_t *>(lean_smem + 4 * PB);
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
-    const long long b = blockIdx.y;
+    const long long b = blockIdx.y + (long long)blockIdx.z * gridDim.y;   // batches beyond 32768 rows spill into grid.z
+    if (b >= a.batch) return;
     const long long g0 = (long long)tile * T;
     const long long rem = a.n_out - g0;
     const int Tt = (int)(rem < T ? rem : T);
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
             for (int lev = top - 1; lev >= 0; lev--)
                 prefetch_l2_span(a.w + (long long)lev * a.lsw + b * a.ldw, g0, Tt + a.ext[lev], a.n_in);
         if (a.pf_dist > 0 && (a.pf_mask & 5)) {
-            const unsigned lin = blockIdx.y * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
+            const unsigned lin = (unsigned)b * (unsigned)a.tiles_per_row + blockIdx.x + (unsigned)a.pf_dist;
             const unsigned fb = lin / (unsigned)a.tiles_per_row;
             if ((int)fb < a.batch) {
                 const long long fg = (long long)(lin - fb * (unsigned)a.tiles_per_row) * T;
@@ -249,6 +260,21 @@ __global__ void __launch_bounds__(256, L <= 12 ? 3 : 2) k_lean_synthesis(const _
         // hand-filled samples (zero padding) of this level's tiles were written before the previous level's closing
         // barrier; only the first level's were written just now
         if (lev == top && a.mode != VW_PERIODIC) __syncthreads();
+        if (a.thr) {
+            // MutableMultiLevelMODWTResult.applyThresholdToArray (:97-118) on the landed tile: W is thresholded exactly once
+            // on its way from HBM to the FMAs, the thresholded coefficients never exist in memory
+            const double lam = __ldg(a.thr + (a.thr_per_row ? b : 0));
+            const bool nonneg = !(lam < 0.0);
+            double2 *w2 = reinterpret_cast<double2 *>(lean_smem + (2 + slot) * PB);
+            const int n2 = (Tt + a.ext[lev]) >> 1;                  // extents are even
+            for (int i = tid; i < n2; i += (int)blockDim.x) {
+                double2 q = w2[i];
+                q.x = nonneg ? vw_threshold_nonneg(q.x, lam, a.thr_soft) : vw_threshold_value(q.x, lam, a.thr_soft);
+                q.y = nonneg ? vw_threshold_nonneg(q.y, lam, a.thr_soft) : vw_threshold_value(q.y, lam, a.thr_soft);
+                w2[i] = q;
+            }
+            __syncthreads();
+        }
         const uint32_t wof8 = sbase + (2 + slot) * PB * 8;
         const int ld2 = a.log2d0 + lev;
         const int d8 = 8 << ld2;
@@ -363,10 +389,11 @@ bool lean_filter_ok(int l, bool qmf) {
 int vw_lean_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt32 &f, int64_t tile, int64_t htot, int64_t hexact,
                     bool use_stage, int nthreads) {
     const bool qmf = vw_is_qmf(f.h, f.g, p.l);
-    if (!lean_filter_ok(p.l, qmf) || p.nlevels > kMaxLev || p.mode == VW_SYMMETRIC) return VW_EUNSUPPORTED;
+    if (!lean_filter_ok(p.l, qmf) || p.nlevels > kMaxLev) return VW_EUNSUPPORTED;
+    if (p.mode == VW_SYMMETRIC && (p.n_in < htot || tile < htot)) return VW_EUNSUPPORTED;   // the mirror patch needs its sources inside the tile
     if (!(ctx->opt_lean & (p.l <= 12 ? 1 : 2))) return VW_EUNSUPPORTED;
     const int64_t tiles_per_row = (p.n_out + tile - 1) / tile;
-    if (p.batch > 65535 || tiles_per_row > 0x7fffffff || tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
+    if (tiles_per_row > 0x7fffffff || tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
     LeanFwd a;
     a.x = p.x; a.ldx = p.ldx; a.w = p.w; a.ldw = p.ldw; a.lsw = p.lsw; a.v = p.v; a.ldv = p.ldv;
     a.n_in = p.n_in; a.t0 = p.t0; a.n_out = p.n_out; a.batch = (int)p.batch;
@@ -389,7 +416,8 @@ int vw_lean_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt32 &f, int64_t
     for (int k = 0; k < VW_LEAN_MAX_L; k++) { a.h[k] = k < p.l ? f.h[k] : 0.0; a.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = (size_t)(2 * pbuf + (use_stage ? 2 * tile : 0)) * 8 + 64;
     if (smem > ctx->smem_optin - 1024) return VW_EUNSUPPORTED;
-    const dim3 grid((unsigned)tiles_per_row, (unsigned)p.batch, 1);
+    const unsigned gy = (unsigned)std::min<int64_t>(p.batch, 32768);
+    const dim3 grid((unsigned)tiles_per_row, gy, (unsigned)((p.batch + gy - 1) / gy));
     int rc = VW_OK;
 #define VW_CALL(LL, QQ)                                                                                          \
     do {                                                                                                         \
@@ -407,18 +435,19 @@ int vw_lean_forward(vw_ctx *ctx, const VwFusedFwd &p, const VwFilt32 &f, int64_t
 int vw_lean_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt32 &f, int64_t tile, int64_t htot, int nthreads) {
     const bool qmf = vw_is_qmf(f.h, f.g, p.l);
     const uint64_t full_mask = p.nlevels >= 64 ? ~0ull : ((1ull << p.nlevels) - 1);
-    if (!lean_filter_ok(p.l, qmf) || p.nlevels > kMaxLev || p.mode == VW_SYMMETRIC || p.has_align || p.thr_dev || !p.v ||
+    if (!lean_filter_ok(p.l, qmf) || p.nlevels > kMaxLev || p.mode == VW_SYMMETRIC || p.has_align || !p.v ||
         (p.detail_mask & full_mask) != full_mask || (tile & 1))
         return VW_EUNSUPPORTED;
     if (!(ctx->opt_lean & (p.l <= 12 ? 1 : 2))) return VW_EUNSUPPORTED;
     const int64_t tiles_per_row = (p.n_out + tile - 1) / tile;
-    if (p.batch > 65535 || tiles_per_row > 0x7fffffff || tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
+    if (tiles_per_row > 0x7fffffff || tiles_per_row * p.batch > 0x7fffffffll) return VW_EUNSUPPORTED;
     LeanInv a;
     a.v = p.v; a.ldv = p.ldv; a.w = p.w; a.ldw = p.ldw; a.lsw = p.lsw; a.out = p.out; a.ldo = p.ldo;
     a.n_in = p.n_in; a.n_out = p.n_out; a.batch = (int)p.batch;
     a.tile = (int)tile; a.htot = (int)htot; a.nlev = p.nlevels; a.log2d0 = p.first_level - 1; a.mode = p.mode;
     a.tiles_per_row = (int)tiles_per_row;
     a.pf_mask = (int)ctx->opt_l2pf;
+    a.thr = p.thr_dev; a.thr_per_row = p.thr_per_row; a.thr_soft = p.thr_soft;
     const int64_t d0 = 1ll << (p.first_level - 1);
     const int64_t dmax = d0 << (p.nlevels - 1);
     for (int i = 0; i < p.nlevels; i++) {
@@ -430,7 +459,8 @@ int vw_lean_inverse(vw_ctx *ctx, const VwFusedInv &p, const VwFilt32 &f, int64_t
     for (int k = 0; k < VW_LEAN_MAX_L; k++) { a.h[k] = k < p.l ? f.h[k] : 0.0; a.g[k] = k < p.l ? f.g[k] : 0.0; }
     const size_t smem = (size_t)(4 * pbuf) * 8 + 64;
     if (smem > ctx->smem_optin - 1024) return VW_EUNSUPPORTED;
-    const dim3 grid((unsigned)tiles_per_row, (unsigned)p.batch, 1);
+    const unsigned gy = (unsigned)std::min<int64_t>(p.batch, 32768);
+    const dim3 grid((unsigned)tiles_per_row, gy, (unsigned)((p.batch + gy - 1) / gy));
     int rc = VW_OK;
 #define VW_CALL(LL, QQ)                                                                                          \
     do {                                                                                                         \

@@ -210,7 +210,7 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
     const bool exact = flags & VW_FLAG_BITEXACT;
     const bool allow_fused = !exact && !(flags & VW_FLAG_NO_FUSE);
     std::vector<VwPlanGroup> plan;
-    ctx->plan_lean_ok = mode != VW_SYMMETRIC;
+    ctx->plan_lean_ok = true;   // the lean analysis takes every boundary mode
     if (allow_fused) vw_plan_levels(ctx, true, l, levels, n, plan);
     else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
     double *buf[2] = {nullptr, nullptr};
@@ -276,7 +276,7 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
     std::vector<VwPlanGroup> plan;
     {
         const uint64_t full = levels >= 64 ? ~0ull : ((1ull << levels) - 1);
-        ctx->plan_lean_ok = mode != VW_SYMMETRIC && !thr_dev && use_approx && (detail_mask & full) == full;
+        ctx->plan_lean_ok = mode != VW_SYMMETRIC && use_approx && (detail_mask & full) == full;
     }
     if (allow_fused) vw_plan_levels(ctx, false, l, levels, n, plan);
     else for (int j = 1; j <= levels; j++) plan.push_back(VwPlanGroup{j, 1, -1, 0.0});
