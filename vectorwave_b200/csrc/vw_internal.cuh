@@ -59,6 +59,7 @@ struct vw_ctx {
     size_t scratch_bytes[2 * kScratch] = {};
     int scratch_set = 0;
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // created on first use by the pipelined host path
+    int64_t opt_pipe_chunks = 8;
     int64_t opt_pipe_min = 64ll << 20;                  // staged bytes from which host calls are chunked and overlapped
     void *pinned = nullptr;  // small pinned mailbox for D2H scalars
     size_t pinned_bytes = 0;

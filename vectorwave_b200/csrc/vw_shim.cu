@@ -377,12 +377,13 @@ int pipe_streams(vw_ctx *ctx) {
     return VW_OK;
 }
 
-// rows per chunk: chunks of >= 16 MB staged bytes, at most 8 of them, at least 2
+// rows per chunk: chunks of >= 16 MB staged bytes, at most `pipe_chunks` of them (the first chunk's H2D and the last
+// chunk's D2H overlap nothing: more chunks = a shorter fill and drain), at least 2
 int64_t pipe_rows(const vw_ctx *ctx, int64_t batch, int64_t n, int levels) {
     const double total = (double)batch * (double)n * 8.0 * (levels + 2);
     if (ctx->opt_pipe_min <= 0 || batch < 2 || total < (double)ctx->opt_pipe_min || ctx->capturing) return 0;
     int64_t chunks = (int64_t)(total / (16.0 * 1048576.0));
-    chunks = std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(chunks, 8), batch));
+    chunks = std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(chunks, std::max<int64_t>(ctx->opt_pipe_chunks, 2)), batch));
     return (batch + chunks - 1) / chunks;
 }
 
@@ -570,6 +571,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
     else if (!strcmp(name, "lean")) ctx->opt_lean = value;
     else if (!strcmp(name, "lean_small")) ctx->opt_lean_small = value;
+    else if (!strcmp(name, "pipe_chunks")) ctx->opt_pipe_chunks = value;   // most chunks a pipelined host call is cut into
     else if (!strcmp(name, "pipe_min")) ctx->opt_pipe_min = value;   // bytes; <= 0 disables the pipelined host path
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;
     else if (!strcmp(name, "zero_copy")) ctx->opt_zero_copy = value;   // bytes up to which pinned host buffers are addressed in place; 0 = always stage       // event pair around every public call (vw_last_timing)
