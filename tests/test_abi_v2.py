@@ -166,6 +166,32 @@ def test_device_resident_result_pipeline(mode):
     res.free()
 
 
+@pytest.mark.parametrize("mode", [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.SYMMETRIC])
+def test_resident_result_through_the_facade(mode):
+    """MultiLevelMODWTTransform.decomposeResident: the facade-level twin of GpuResidentResult.java -- same getters as the
+    host-backed result, reconstruct / partial reconstruct / thresholds on the device."""
+    name, n, levels = "db4", 3000, 5
+    h, g, wid = filters(name)
+    x = np.random.default_rng(8).standard_normal(n)
+    t = vw.MultiLevelMODWTTransform(vw.get_wavelet(name), mode)
+    host = t.decompose(x, levels)
+    res = t.decomposeResident(x, levels)
+    assert res.getLevels() == levels and res.getSignalLength() == n
+    tol = REL * float(np.max(np.abs(x)))
+    for j in range(1, levels + 1):
+        np.testing.assert_allclose(res.getDetailCoeffsAtLevel(j), host.getDetailCoeffsAtLevel(j), rtol=0, atol=tol)
+        assert abs(res.getDetailEnergyAtLevel(j) - host.getDetailEnergyAtLevel(j)) <= 1e-12 * host.getDetailEnergyAtLevel(j)
+    np.testing.assert_allclose(res.reconstruct(), t.reconstruct(host), rtol=0, atol=tol)
+    np.testing.assert_allclose(t.reconstructFromLevel(res, 3), t.reconstructFromLevel(host, 3), rtol=0, atol=tol)
+    thr = res.applyUniversalThreshold(True)
+    dref, tref = cref.swt_denoise(x, h, g, levels, mode.value, wid, -1.0, True)
+    assert abs(thr - tref) <= 1e-12 * tref
+    np.testing.assert_allclose(res.reconstruct(), dref, rtol=0, atol=tol)
+    with pytest.raises(vw.IllegalArgumentException):
+        res.getDetailCoeffsAtLevel(levels + 1)
+    res.close()
+
+
 def test_graph_replay_of_a_small_transform():
     """Config #1's shape (1 x 4096, db4, J = 1) recorded once -- H2D, kernel, two D2H copies -- and replayed as one CUDA
     graph launch on new data in the same pinned buffers."""

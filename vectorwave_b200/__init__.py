@@ -11,7 +11,7 @@ from .errors import (ErrorCode, IllegalArgumentException, InvalidArgumentExcepti
                      NativeEngineError, NullPointerException, WaveletTransformException)
 from .modwt import (MODWTResult, MODWTTransform, MODWTTransformFactory, MultiLevelMODWTResult,  # noqa: F401
                     MultiLevelMODWTTransform, MutableMultiLevelMODWTResult, ParallelMultiLevelMODWT,
-                    SymmetricAlignmentStrategy)
+                    ResidentMultiLevelMODWTResult, SymmetricAlignmentStrategy)
 from .ops import WaveletOperations  # noqa: F401
 from .streaming import BatchStreamingMODWT  # noqa: F401
 from .streaming_core import InvalidStateException, MODWTStreamingTransform  # noqa: F401

@@ -447,7 +447,35 @@ class MultiLevelMODWTTransform:
             raise NullPointerException("signal cannot be null")
         return self._decompose(signal, levels, True)
 
+    def decomposeResident(self, signal, levels=None, result=None):
+        """decomposeMutable with the coefficients kept in HBM (vw_modwt_decompose_h): a ResidentMultiLevelMODWTResult
+        copies a level to the host only when asked, thresholds / energies run on the device, `reconstruct()` moves 8
+        B/sample back.  `result`: an earlier resident result of the same shape whose device storage is reused."""
+        if signal is None:
+            raise NullPointerException("signal cannot be null")
+        x = _as_signal(signal)
+        if x.ndim != 1:
+            raise IllegalArgumentException("decompose takes one 1-D signal")
+        n = _length(x)
+        if n == 0:
+            raise InvalidSignalException("Signal cannot be empty for multi-level MODWT", ErrorCode.VAL_EMPTY)
+        max_levels = self._calculate_max_levels(n)
+        if levels is None:
+            levels = max_levels
+        if levels < 1 or levels > max_levels:
+            raise InvalidArgumentException(
+                f"Invalid number of decomposition levels: {levels} (maximum {max_levels} for signal length {n})",
+                ErrorCode.CFG_INVALID_DECOMPOSITION_LEVEL)
+        handle = self._eng().decompose_resident(x, self._hs, self._gs, levels, self.boundaryMode.value,
+                                                result=result._handle if result is not None else None,
+                                                flags=_native.FLAG_CHECK_FINITE | self._flags)
+        return ResidentMultiLevelMODWTResult(self, handle)
+
     def _reconstruct(self, result, detail_mask, use_approx):
+        if isinstance(result, ResidentMultiLevelMODWTResult):
+            align, order = multilevel_alignment(self.wavelet, self.boundaryMode, result.getLevels())
+            return result._handle.reconstruct(self._hrs, self._grs, self.boundaryMode.value, align, order, detail_mask,
+                                              use_approx)[0]
         align, order = multilevel_alignment(self.wavelet, self.boundaryMode, result.getLevels())
         return self._eng().inverse(result._w, result._v, self._hrs, self._grs, self.boundaryMode.value, align, order,
                                    detail_mask, use_approx, flags=self._flags)
@@ -485,6 +513,68 @@ class MultiLevelMODWTTransform:
 # ---------------------------------------------------------------------------------------------
 # ParallelMultiLevelMODWT / MODWTTransformFactory (thin host classes over the same engine calls)
 # ---------------------------------------------------------------------------------------------
+class ResidentMultiLevelMODWTResult:
+    """MutableMultiLevelMODWTResult (CORE/modwt/MutableMultiLevelMODWTResult.java:30-123) backed by a device-resident
+    vw_result: the Python twin of java/.../modwt/GpuResidentResult.java."""
+
+    def __init__(self, transform, handle):
+        self._t, self._handle = transform, handle
+
+    def getLevels(self):
+        return self._handle.shape()[2]
+
+    def getSignalLength(self):
+        return self._handle.shape()[1]
+
+    def _check(self, level):
+        if level < 1 or level > self.getLevels():
+            raise IllegalArgumentException(f"Level must be between 1 and {self.getLevels()}, got: {level}")
+
+    def getDetailCoeffsAtLevel(self, level):
+        self._check(level)
+        return self._handle.get_level(level)[0]
+
+    def getApproximationCoeffs(self):
+        return self._handle.get_level(0)[0]
+
+    def setDetailCoeffs(self, level, coeffs):
+        self._check(level)
+        self._handle.set_level(level, np.asarray(coeffs, dtype=np.float64).reshape(1, -1))
+
+    def setApproximationCoeffs(self, coeffs):
+        self._handle.set_level(0, np.asarray(coeffs, dtype=np.float64).reshape(1, -1))
+
+    def applyThreshold(self, level, threshold, soft):
+        if level == 0:                                        # the reference thresholds the approximation for level 0 (:84-86)
+            v = self.getApproximationCoeffs()
+            a = np.abs(v)
+            self.setApproximationCoeffs(np.where(a > threshold, np.sign(v) * (a - threshold), 0.0) if soft
+                                        else np.where(a <= threshold, 0.0, v))
+            return
+        self._check(level)
+        self._handle.threshold(level, float(threshold), soft)
+
+    def applyUniversalThreshold(self, soft=True):
+        """VectorWaveSwtAdapter.applyUniversalThreshold (:505-520) on the resident coefficients; returns the threshold."""
+        return float(self._handle.universal_threshold(soft)[0])
+
+    def getDetailEnergyAtLevel(self, level):
+        self._check(level)
+        return float(self._handle.energy(level)[0])
+
+    def getApproximationEnergy(self):
+        return float(self._handle.energy(0)[0])
+
+    def getTotalEnergy(self):
+        return sum(self.getDetailEnergyAtLevel(j) for j in range(1, self.getLevels() + 1)) + self.getApproximationEnergy()
+
+    def reconstruct(self):
+        return self._t.reconstruct(self)
+
+    def close(self):
+        self._handle.free()
+
+
 class ParallelMultiLevelMODWT:
     """CORE/modwt/ParallelMultiLevelMODWT.java:84-176.  The reference runs the h and g convolutions of a level on an
     executor; here the level is one kernel launch anyway, so only its observable quirks are mirrored: any
