@@ -449,6 +449,60 @@ def extra_span(c, reps=4):
     return out
 
 
+def extra_span_one_thread(c, reps=4):
+    """The same span-sharded 2^28 coif5 J=10 transform driven the way a JVM would: ONE host thread, every GPU of the job
+    through vw_init_multi / vw_modwt_forward_sharded / vw_modwt_inverse_sharded (halos as peer copies over NVLink).  Runs on
+    rank 0 while the other ranks wait; host wall clock around synchronous calls (each returns when every device is done)."""
+    from vectorwave_b200 import _native
+    torch, vw = c.torch, c.vw
+    world = c.world
+    n_total, levels = 1 << 28, 10
+    n_local = n_total // world
+    wv = vw.Coiflet.COIF5
+    hs, gs = wv.lowPassDecomposition() * S, wv.highPassDecomposition() * S
+    plan = _native.span_plan(hs.size, levels, n_local, world)
+    lead, lead_w, pad = int(plan.lead), int(plan.lead_w), int(plan.pad)
+    row = lead_w + n_local + pad
+    devices = list(range(world))
+    me = _native.MultiEngine(devices)
+    try:
+        xext, w, v, xo = [], [], [], []
+        for d in devices:
+            dev = torch.device("cuda", d)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(42 + d)
+            e = torch.empty(lead + n_local, dtype=torch.float64, device=dev)
+            e[lead:] = torch.randn(n_local, dtype=torch.float64, device=dev, generator=gen)
+            xext.append(e)
+            w.append(torch.empty((levels, row), dtype=torch.float64, device=dev))
+            v.append(torch.empty(n_local + pad, dtype=torch.float64, device=dev))
+            xo.append(torch.empty(n_local, dtype=torch.float64, device=dev))
+        for d in devices:
+            torch.cuda.synchronize(d)
+        l0 = me.launch_count()
+        ex_f = me.forward(plan, xext, hs, gs, 0, w, v, timed=True)
+        ex_i = me.inverse(plan, w, v, hs, gs, 0, 0, xo, timed=True)
+        launches = me.launch_count() - l0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            me.forward(plan, xext, hs, gs, 0, w, v)
+            me.inverse(plan, w, v, hs, gs, 0, 0, xo)
+        ms = (time.perf_counter() - t0) / reps * 1e3
+        rt = max(float((xo[d] - xext[d][lead:]).abs().max()) for d in devices)
+    finally:
+        me.close()
+    assert rt < 1e-9, f"sharded ABI round trip error {rt}"
+    model = c.peak / (48.0 * levels) * world
+    out = {"workload": "single2p28_coif5_J10", "scaling": "strong", "driver": "one host thread, vw_init_multi over "
+           f"{world} device(s), peer-copy halo exchange", "value": n_total / ms * 1e-6, "unit": UNIT, "ms_per_step": ms,
+           "halo_exchange_ms": {"analysis": ex_f, "synthesis": ex_i, "note": "device time of the slowest receiving copy, CUDA events"},
+           "gpu_launches_per_step": launches, "round_trip_max_abs_err": rt, "timing": "host wall clock around synchronous calls",
+           "roofline_model_gsamples": model, "frac_of_roofline_model": n_total / ms * 1e-6 / model}
+    del xext, w, v, xo
+    c.free()
+    return out
+
+
 def extra_latency(local_rank):
     exe = os.path.join(ROOT, "tools", "_build", "latency")
     if not os.path.exists(exe):
@@ -543,6 +597,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     dev = torch.device("cuda", local_rank)
     eng = vw.Engine.get(local_rank)
     peak, peak_src = measured_peaks()
@@ -729,6 +784,19 @@ def main():
             extra["batch_strong_c3"]["scaling"] = "strong"
             extra["batch_strong_c3"]["sharding"] = f"1024 signals split by signal over {world} ranks, no communication"
         guarded("span", lambda: extra_span(c))
+        # the JVM's way of driving the same transform: rank 0 alone, one host thread over all the job's GPUs.  The other
+        # ranks wait on a CPU (gloo) barrier: an NCCL barrier is a kernel spinning on their GPU, which would time-slice
+        # against rank 0's kernels there (measured: 34 ms per step instead of 13)
+        c.free()
+        c.barrier()
+        if rank == 0:
+            try:
+                extra["span_one_host_thread"] = extra_span_one_thread(c)
+            except Exception as ex:
+                extra["span_one_host_thread"] = {"failed": f"{type(ex).__name__}: {ex}"[:300]}
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        c.barrier()
         if world > 1:
             # what the box's PCIe fabric gives when every rank copies at once (e2e at N > 1 is bound by this, not by the engine)
             c.barrier()

@@ -361,15 +361,14 @@ int vw_modwt_forward_sharded(vw_multi *m, const vw_span_plan *plan, double *cons
         vw_ctx *c = m->ctx[r];
         DeviceGuard g(c, "vw_modwt_forward_sharded");
         const int left = (r + P - 1) % P;
-        cudaError_t e = cudaEventRecord(m->ev_t0[r], c->stream);
-        if (e == cudaSuccess) {
-            if (r == 0 && mode == VW_ZERO_PADDING) e = cudaMemsetAsync(xext[r], 0, (size_t)lead * 8, c->stream);
-            else {
-                if (left != r) e = cudaStreamWaitEvent(c->stream, m->ev_ready[left], 0);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyPeerAsync(xext[r], c->device, xext[left] + n, m->ctx[left]->device, (size_t)lead * 8, c->stream);
-            }
-        }
+        // the timing events bracket the copy alone: the wait for the neighbour's data is in front of them
+        cudaError_t e = cudaSuccess;
+        const bool open_end = r == 0 && mode == VW_ZERO_PADDING;
+        if (!open_end && left != r) e = cudaStreamWaitEvent(c->stream, m->ev_ready[left], 0);
+        if (e == cudaSuccess) e = cudaEventRecord(m->ev_t0[r], c->stream);
+        if (e == cudaSuccess)
+            e = open_end ? cudaMemsetAsync(xext[r], 0, (size_t)lead * 8, c->stream)
+                         : cudaMemcpyPeerAsync(xext[r], c->device, xext[left] + n, m->ctx[left]->device, (size_t)lead * 8, c->stream);
         if (e == cudaSuccess) e = cudaEventRecord(m->ev_t1[r], c->stream);
         if ((rc = multi_from_ctx(m, r, vw_cuda_check(c, e, "halo exchange (analysis)")))) return rc;
     }
@@ -415,12 +414,11 @@ int vw_modwt_inverse_sharded(vw_multi *m, const vw_span_plan *plan, double *cons
         DeviceGuard g(c, "vw_modwt_inverse_sharded");
         const int right = (r + 1) % P;
         const bool open_end = r == P - 1 && mode == VW_ZERO_PADDING;
-        cudaError_t e = cudaEventRecord(m->ev_t0[r], c->stream);
-        if (e == cudaSuccess && !open_end) {
-            if (right != r) e = cudaStreamWaitEvent(c->stream, m->ev_ready[right], 0);
-            if (e == cudaSuccess)
-                e = cudaMemcpyPeerAsync(m->msg_recv[r], c->device, m->msg_send[right], m->ctx[right]->device, msg_bytes, c->stream);
-        }
+        cudaError_t e = cudaSuccess;
+        if (!open_end && right != r) e = cudaStreamWaitEvent(c->stream, m->ev_ready[right], 0);
+        if (e == cudaSuccess) e = cudaEventRecord(m->ev_t0[r], c->stream);
+        if (e == cudaSuccess && !open_end)
+            e = cudaMemcpyPeerAsync(m->msg_recv[r], c->device, m->msg_send[right], m->ctx[right]->device, msg_bytes, c->stream);
         if (e == cudaSuccess) e = cudaEventRecord(m->ev_t1[r], c->stream);
         if ((rc = multi_from_ctx(m, r, vw_cuda_check(c, e, "halo exchange (synthesis)")))) return rc;
         if ((rc = multi_from_ctx(m, r, vw_span_unpack_inverse(c, plan, open_end ? nullptr : m->msg_recv[r], w[r], row_stride, v[r],
