@@ -185,7 +185,8 @@ int finish(vw_ctx *ctx, uint32_t flags, bool host_io) {
         if (ctx->scratch_stream == ctx->stream) ctx->scratch_pending = false;   // the stream the scratch was last used on has drained
         return rc;
     }
-    // returning with work in flight: mark where the scratch buffers become free again
+    // returning with work in flight: mark where the scratch buffers become free again (the outermost call does it once)
+    if (ctx->call_depth > 1) return VW_OK;
     if (!ctx->scratch_event) {
         int rc = vw_cuda_check(ctx, cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming), "scratch event");
         if (rc) return rc;
