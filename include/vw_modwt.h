@@ -127,6 +127,12 @@ VW_API int vw_describe_plan(int forward, int32_t l, int32_t levels, int64_t n, i
 /* The same schedule as numbers: group g covers levels first[g] .. first[g]+nlev[g]-1.  Returns the group count
  * (<= cap) or a negative vw_status.  Used by the span-sharded host code to align halo exchanges with launches. */
 VW_API int vw_plan_query(int forward, int32_t l, int32_t levels, int64_t n, int32_t *first, int32_t *nlev, int32_t cap);
+/* Paraunitary lattice of the quadrature-mirror pair (hs, gs) as the column kernels of long filters use it (csrc/vw_lattice.cu):
+ * writes t_1 .. t_{l/2-1} then the 2 x 2 base matrix row-major into coef[0..cap) and the largest deviation of the lattice's
+ * taps from the given ones into *tap_err (either may be NULL).  Returns the number of coefficients (l/2 + 3) when the
+ * lattice reproduces the taps to rounding and the engine will use it, 0 when the pair keeps the direct form, or a
+ * negative vw_status.  Pure host logic: needs no device. */
+VW_API int vw_lattice_query(const double *hs, const double *gs, int32_t l, double *coef, int32_t cap, double *tap_err);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 VW_API int64_t vw_launch_count(const vw_ctx *ctx);
 

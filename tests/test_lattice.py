@@ -1,0 +1,227 @@
+"""The lattice form of the long-filter column kernels (csrc/vw_lattice.cu, csrc/vw_column.cu).
+
+CPU part: the host-side factorisation -- which reference tables fit a paraunitary lattice to rounding (coif5 does,
+sym8 / db8 / db4 do not and keep the direct form), and a numpy evaluation of the cascade with the returned coefficients
+against the oracle's direct sums (analysis and synthesis), so the algebra the kernels implement is pinned without a GPU.
+GPU part: the coif5 column levels in lattice form against the oracle in every boundary mode, on ragged lengths, batches,
+span calls and the threshold-on-load synthesis, and against the direct-form kernels (option "lattice" = 0)."""
+import numpy as np
+import pytest
+
+from oracle import cref, nptwin
+from oracle.wavelets import TABLES, filters
+from vectorwave_b200 import _native
+
+S = nptwin.S
+REL = 1e-12
+
+
+def _lattice(name):
+    h, g, _ = filters(name)
+    return _native.lattice_query(h * S, g * S)
+
+
+def test_coif5_fits_a_lattice_to_rounding_and_short_or_inexact_tables_do_not():
+    coef, err = _lattice("coif5")
+    assert coef is not None and coef.size == 15 + 3
+    assert err <= 2e-16                      # every tap of h and g reproduced to half an ulp of the largest tap
+    for name in ("db4", "db8", "sym8", "coif2", "coif3", "db10"):
+        coef, err = _lattice(name)
+        assert coef is None and err > 2e-16, name      # decimal tables that are not orthonormal to rounding
+
+
+def test_lattice_query_rejects_pairs_that_are_not_quadrature_mirrors():
+    h, g, _ = filters("coif5")
+    g2 = g.copy()
+    g2[3] *= 1.0 + 1e-15
+    coef, err = _native.lattice_query(h * S, g2 * S)
+    assert coef is None
+
+
+def _expand(coef):
+    """taps of E(z) = S_{K-1} Lam ... S_1 Lam B from the coefficients the kernels get (float64 arithmetic is enough
+    to see 1e-15)"""
+    k = coef.size - 3
+    t, b = coef[:k - 1], coef[k - 1:].reshape(2, 2)
+    e = [b.astype(np.longdouble)]
+    for tk in t.astype(np.longdouble):
+        f = [np.zeros((2, 2), dtype=np.longdouble) for _ in range(len(e) + 1)]
+        for n, en in enumerate(e):
+            f[n][0, :] = en[0, :]
+            f[n + 1][1, :] = en[1, :]
+        s = np.array([[1, tk], [-tk, 1]], dtype=np.longdouble)
+        e = [s @ fn for fn in f]
+    h = np.array([x for en in e for x in (en[0, 0], en[0, 1])])
+    g = np.array([x for en in e for x in (en[1, 0], en[1, 1])])
+    return h, g
+
+
+def test_coefficients_expand_back_to_the_reference_table():
+    h, g, _ = filters("coif5")
+    coef, _ = _lattice("coif5")
+    hh, gg = _expand(coef)
+    assert float(np.max(np.abs(hh - (h * S).astype(np.longdouble)))) <= 2e-16
+    assert float(np.max(np.abs(gg - (g * S).astype(np.longdouble)))) <= 2e-16
+
+
+def _analysis_rows(u, coef):
+    """the per-row recurrence of k_column_analysis_lat on one periodic column"""
+    k = coef.size - 3
+    t, b = coef[:k - 1], coef[k - 1:]
+    n = u.size
+    v, w = np.zeros(n), np.zeros(n)
+    dl = np.zeros((k - 1, 2))
+    uprev = 0.0
+    for q in range(-30, n):
+        x = u[q % n]
+        aa = b[0] * x + b[1] * uprev
+        bb = b[2] * x + b[3] * uprev
+        uprev = x
+        for s in range(k - 1):
+            bd = dl[s, q & 1]
+            dl[s, q & 1] = bb
+            aa, bb = aa + t[s] * bd, bd - t[s] * aa
+        if q >= 0:
+            v[q], w[q] = aa, bb
+    return v, w
+
+
+def _synthesis_rows(v, w, coef):
+    """the per-row recurrence of k_column_synthesis_lat on one periodic column"""
+    k = coef.size - 3
+    t, b = coef[:k - 1], coef[k - 1:]
+    n, l = v.size, 2 * k
+    out = np.zeros(n)
+    dl = np.zeros((k - 1, 2))
+    y0prev = 0.0
+    for m in range(n + l - 1):
+        aa, bb = v[m % n], w[m % n]
+        for s in range(k - 2, -1, -1):
+            an, bb = aa - t[s] * bb, bb + t[s] * aa
+            aa = dl[s, m & 1]
+            dl[s, m & 1] = an
+        y0 = b[0] * aa + b[2] * bb
+        y1 = b[1] * aa + b[3] * bb
+        if m - (l - 1) >= 0:
+            out[m - (l - 1)] = y0prev + y1
+        y0prev = y0
+    return out
+
+
+def test_numpy_cascade_equals_the_oracle_direct_sums():
+    h, g, wid = filters("coif5")
+    coef, _ = _lattice("coif5")
+    x = np.random.default_rng(5).standard_normal(1536)
+    wo, vo = cref.decompose(x, h, g, 1, 0)
+    v, w = _analysis_rows(x, coef)
+    t = 1e-14 * float(np.max(np.abs(x)))
+    assert float(np.max(np.abs(v - vo))) <= t and float(np.max(np.abs(w - wo[0]))) <= t
+    ref = cref.reconstruct(wo, vo, h, g, 0, wid)
+    assert float(np.max(np.abs(_synthesis_rows(vo, wo[0], coef) - ref))) <= t
+
+
+# ---- GPU -------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture()
+def eng():
+    import vectorwave_b200 as vw
+    e = vw.Engine.get()
+    yield e
+    for k, v in (("lattice", 1), ("colmin", 0), ("tile", 0), ("fuse", 0)):
+        e.set_option(k, v)
+
+
+def _both(eng, fn):
+    """fn() with the lattice kernels and with the direct-form kernels"""
+    eng.set_option("lattice", 1)
+    a = fn()
+    eng.set_option("lattice", 0)
+    b = fn()
+    eng.set_option("lattice", 1)
+    return a, b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("b,n,levels", [(1, 65536, 8), (3, 40001, 7), (2, 9000, 5), (1, 1 << 20, 10)])
+def test_coif5_column_levels_in_lattice_form_against_the_oracle(eng, mode, b, n, levels):
+    import vectorwave_b200 as vw
+    from vectorwave_b200.modwt import multilevel_alignment
+    h, g, wid = filters("coif5")
+    hs, gs = h * S, g * S
+    x = np.random.default_rng(n + mode).standard_normal((b, n))
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(vw.get_wavelet("coif5"), bm, levels)
+    l0 = eng.launch_count()
+    (w, v), (wd, vd) = _both(eng, lambda: eng.forward(x, hs, gs, levels, mode))
+    assert eng.launch_count() > l0
+    w, v, wd, vd = (np.asarray(a) for a in (w, v, wd, vd))
+    t = REL * float(np.max(np.abs(x)))
+    rows = range(b) if n <= 70000 else [b - 1]
+    for i in rows:
+        wo, vo = cref.decompose(x[i], h, g, levels, mode)
+        assert float(np.max(np.abs(w[:, i, :] - wo))) <= t
+        assert float(np.max(np.abs(v[i] - vo))) <= t
+        ref = cref.reconstruct(wo, vo, h, g, mode, wid)
+        xr, xrd = _both(eng, lambda: np.asarray(eng.inverse(wo[:, None, :].copy(), vo[None, :].copy(), hs, gs, mode, align, order)))
+        tr = REL * max(float(np.max(np.abs(ref))), float(np.max(np.abs(x))))
+        assert float(np.max(np.abs(xr[0] - ref))) <= tr
+        assert float(np.max(np.abs(xrd[0] - ref))) <= tr
+    # the two forms agree far inside the parity bar (they differ by rounding only)
+    assert float(np.max(np.abs(w - wd))) <= 0.05 * t and float(np.max(np.abs(v - vd))) <= 0.05 * t
+
+
+@pytest.mark.gpu
+def test_lattice_is_what_runs_for_coif5_and_only_for_it(eng):
+    """A filter whose table fits no lattice must give bit-identical results whether the option is on or off (nothing of
+    the lattice path may touch it); coif5 must differ in the last bits (the lattice really ran) yet stay within rounding."""
+    x = np.random.default_rng(3).standard_normal((2, 1 << 17))
+    for name, same in (("db10", True), ("sym8", True), ("coif5", False)):
+        h, g, _ = filters(name)
+        (w, v), (wd, vd) = _both(eng, lambda: eng.forward(x, h * S, g * S, 8, 0))
+        w, wd = np.asarray(w), np.asarray(wd)
+        if same:
+            assert np.array_equal(w, wd), name
+        else:
+            assert not np.array_equal(w, wd)
+            assert float(np.max(np.abs(w - wd))) <= 1e-14 * float(np.max(np.abs(x)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+def test_coif5_swt_denoise_thresholds_on_load_in_the_lattice_synthesis(eng, mode):
+    import vectorwave_b200 as vw
+    from vectorwave_b200.modwt import multilevel_alignment
+    h, g, wid = filters("coif5")
+    n, levels = 1 << 16, 6
+    x = np.random.default_rng(11).standard_normal((2, n))
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(vw.get_wavelet("coif5"), bm, levels)
+    den, thr = eng.denoise(x, h * S, g * S, levels, mode, align, order, -1.0, True)
+    den = np.asarray(den)
+    for i in range(2):
+        dref, tref = cref.swt_denoise(x[i], h, g, levels, mode, wid, -1.0, True)
+        assert abs(float(np.asarray(thr)[i]) - tref) <= 1e-12 * tref
+        assert float(np.max(np.abs(den[i] - dref))) <= REL * float(np.max(np.abs(x)))
+
+
+@pytest.mark.gpu
+def test_coif5_span_calls_in_lattice_form_equal_the_unsharded_transform(eng):
+    """rank-local span call (input = [halo | owned], VW_MODE_LINEAR inside) through the lattice column kernels"""
+    import torch
+    h, g, _ = filters("coif5")
+    hs, gs = h * S, g * S
+    n, level = 1 << 17, 6
+    x = np.random.default_rng(2).standard_normal(n)
+    # V_5 of the whole signal, then level 6 computed on the second half from [halo | owned] of V_5
+    w, v = eng.forward(x, hs, gs, level - 1, 0)
+    v5 = np.asarray(v).reshape(-1)
+    wf, vf = eng.forward(x, hs, gs, level, 0)
+    halo = eng.span_halo(30, level, 1)
+    lo = n // 2
+    ext = torch.as_tensor(np.ascontiguousarray(v5[lo - halo:]), device="cuda")
+    ws, vs = eng.forward_span(ext, halo, hs, gs, level, 1)
+    torch.cuda.synchronize()
+    t = REL * float(np.max(np.abs(x)))
+    assert float(np.max(np.abs(ws.cpu().numpy().reshape(-1) - np.asarray(wf)[level - 1].reshape(-1)[lo:]))) <= t
+    assert float(np.max(np.abs(vs.cpu().numpy().reshape(-1) - np.asarray(vf).reshape(-1)[lo:]))) <= t

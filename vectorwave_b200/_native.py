@@ -80,6 +80,7 @@ SIGNATURES = {
     "vw_launch_count": (_i64, [_vp]),
     "vw_plan_query": (C.c_int, [C.c_int, _i32, _i32, _i64, C.POINTER(_i32), C.POINTER(_i32), _i32]),
     "vw_describe_plan": (C.c_int, [C.c_int, _i32, _i32, _i64, _i64, _i32, C.c_char_p, C.c_size_t]),
+    "vw_lattice_query": (C.c_int, [_dp, _dp, _i32, _dp, _i32, _dp]),
     "vw_alloc_pinned": (_vp, [C.c_size_t]),
     "vw_free_pinned": (None, [_vp]),
     "vw_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -168,6 +169,22 @@ def describe_plan(forward, l, levels, n, tile=0, fuse=0):
     if rc < 0:
         raise IllegalArgumentException(f"vw_describe_plan failed: {rc}")
     return buf.value.decode()
+
+
+def lattice_query(hs, gs):
+    """(coefficients or None, tap_err): the paraunitary lattice the column kernels of long filters would use for the
+    scaled pair (hs, gs) -- t_1..t_{K-1} then the 2 x 2 base matrix -- or None when the pair keeps the direct form
+    (host logic only; csrc/vw_lattice.cu)."""
+    import numpy as np
+    hs = np.ascontiguousarray(hs, dtype=np.float64)
+    gs = np.ascontiguousarray(gs, dtype=np.float64)
+    coef = np.zeros(64, dtype=np.float64)
+    err = C.c_double(0.0)
+    rc = load_library().vw_lattice_query(hs.ctypes.data_as(_dp), gs.ctypes.data_as(_dp), int(hs.size), coef.ctypes.data_as(_dp), 64,
+                                          C.byref(err))
+    if rc < 0:
+        raise IllegalArgumentException(f"vw_lattice_query failed: {rc}")
+    return (coef[:rc].copy() if rc > 0 else None), err.value
 
 
 def plan_groups(forward, l, levels, n):

@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value
+constexpr int kCR = 72;        // granularity of rows_per_chunk: a multiple of every col_rows<L>::value (the lattice kernels pass their own)
 #ifndef VW_COL_RA
 #define VW_COL_RA 10
 #endif
@@ -320,6 +320,232 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? VW_COL_CS : ((L >= 16) 
     }
 }
 
+// ---- lattice form (long quadrature-mirror pairs whose taps fit a paraunitary lattice: vw_lattice.cu) -------------
+// Same thread / chunk / column geometry and the same loads and stores as the direct kernels above; only the arithmetic
+// differs.  Per column the undilated sequence u[q] goes through  E(z) = S_{K-1} Lam ... S_1 Lam B  (Lam delays the second
+// channel by TWO rows: the undecimated transform is two interleaved decimated ones, rows of equal parity share a delay
+// line): per row one 2 x 2 product and K-1 stages of two FMAs give V[q] and W[q] together -- L + 2 FP64 instructions per
+// sample where the direct form spends 2L, which moves coif5 from the FP64 roof to the HBM roof (24 B/sample).  State per
+// thread: 2 (K-1) delayed values + the previous input row -- the size of the direct form's L-1 window, but nothing shifts:
+// with R even every delay slot is a fixed register of the unrolled body.
+struct ColLat { double b[4]; double t[VW_LATTICE_MAX_K - 1]; };
+
+constexpr int kLR = 10;   // rows per block (even)
+
+template <int K>
+__global__ void __launch_bounds__(kCThreads, 3) k_column_analysis_lat(const __grid_constant__ ColArgs a, const __grid_constant__ ColLat c) {
+    constexpr int L = 2 * K, R = kLR;
+    constexpr int LEAD = ((L - 1 + R - 1) / R) * R;   // warm-up rows before the chunk: whole blocks, nothing of them is stored
+    static_assert(R % 2 == 0 && LEAD % 2 == 0, "row parity must be a compile-time property of the unrolled body");
+    const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
+    const int d = (int)a.d;
+    const long long chunk = gid / a.d;
+    const int col = (int)(gid - chunk * a.d);
+    if (chunk >= a.chunks) return;
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const long long rows = (a.n_out - col + a.d - 1) / a.d;
+        const long long q0 = chunk * a.rows_per_chunk;
+        const long long left64 = rows - q0;
+        if (left64 <= 0) continue;
+        const int left = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const long long p = a.t0 + col + q0 * a.d;            // position of the chunk's first output row
+        const long long p_lead = p - (long long)LEAD * a.d;   // position of the first warm-up row
+        const double *x = a.x + b * a.ldx;
+        const bool lead_plain = p_lead >= 0;                   // warm-up rows inside the row: plain loads
+        const long long step = (long long)d * (8 * R);
+        // all three pointers address row 0 of the CURRENT block; v / w are not dereferenced during the warm-up
+        const char *xp = reinterpret_cast<const char *>(x + p) - (long long)d * (8 * LEAD);
+        char *vp = reinterpret_cast<char *>(a.v + b * a.ldv + (p - a.t0)) - (long long)d * (8 * LEAD);
+        char *wp = reinterpret_cast<char *>(a.w + b * a.ldw + (p - a.t0)) - (long long)d * (8 * LEAD);
+        double dl[K - 1][2];
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) { dl[k][0] = 0.0; dl[k][1] = 0.0; }
+        double uprev = 0.0;     // the row before the first warm-up row: nothing that is stored depends on it
+        int lead = LEAD;        // warm-up rows still ahead (counted from the current block)
+        int todo = left;        // output rows still owed once the warm-up is over
+        double nxt[R];
+        if (lead_plain) {
+#pragma unroll
+            for (int r = 0; r < R; r++) nxt[r] = __ldg(row_ptr(xp, d, r));
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) nxt[r] = ext_load<true>(x, p_lead + (long long)r * a.d, a.n_in, a.mode);
+        }
+        while (todo > 0) {
+            double cur[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) cur[r] = nxt[r];
+            // next block: still warm-up (maybe outside the row), or output rows (always inside [0, n_in))
+            const int avail = lead > 0 ? todo + lead - R : todo - R;     // rows that exist from the next block's row 0 on
+            if (lead > R && !lead_plain) {
+                const long long pn = p - (long long)(lead - R) * a.d;
+#pragma unroll
+                for (int r = 0; r < R; r++) nxt[r] = ext_load<true>(x, pn + (long long)r * a.d, a.n_in, a.mode);
+            } else if (avail >= R) {
+#pragma unroll
+                for (int r = 0; r < R; r++) nxt[r] = ldg_early(row_ptr(xp, d, R + r));
+            } else if (avail > 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++) nxt[r] = r < avail ? __ldg(row_ptr(xp, d, R + r)) : 0.0;
+            }
+            double ah[R], ag[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const double xv = cur[r];
+                double aa = fma(c.b[1], uprev, c.b[0] * xv);
+                double bb = fma(c.b[3], uprev, c.b[2] * xv);
+                uprev = xv;
+#pragma unroll
+                for (int k = 0; k < K - 1; k++) {
+                    const double bd = dl[k][r & 1];
+                    dl[k][r & 1] = bb;
+                    const double an = fma(c.t[k], bd, aa);
+                    bb = fma(-c.t[k], aa, bd);
+                    aa = an;
+                }
+                ah[r] = aa; ag[r] = bb;
+            }
+            if (lead <= 0) {
+                if (todo >= R) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) { *row_ptr(vp, d, r) = ah[r]; *row_ptr(wp, d, r) = ag[r]; }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if (r < todo) { *row_ptr(vp, d, r) = ah[r]; *row_ptr(wp, d, r) = ag[r]; }
+                }
+                todo -= R;
+            }
+            lead -= R;
+            xp += step; vp += step; wp += step;
+        }
+    }
+}
+
+// out[o] = y0(o + L - 2) + y1(o + L - 1) with  y(m) = B^T D S_1^T D ... D S_{K-1}^T [V'[m]; W'[m]]  (D delays the FIRST channel by
+// two rows): the transposed cascade.  Input row m completes output row m - (L-1), exactly like the transposed direct form
+// above, so the chunk bookkeeping (lead, in_left, the output pointer that starts L-1 rows early) is shared with it.
+template <int K, bool EDGE, bool THR>
+__device__ __forceinline__ void col_synth_chunk_lat(const ColArgs &a, const ColLat &c, const double *__restrict__ v,
+                                                    const double *__restrict__ w, char *op, int d, int nout, long long pin,
+                                                    double lam) {
+    constexpr int L = 2 * K, R = kLR;
+    static_assert(R % 2 == 0, "row parity must be a compile-time property of the unrolled body");
+    const bool thr_nonneg = !(lam < 0.0);
+    double dl[K - 1][2];
+#pragma unroll
+    for (int k = 0; k < K - 1; k++) { dl[k][0] = 0.0; dl[k][1] = 0.0; }
+    double y0prev = 0.0;
+    int in_left = nout + (L - 1);
+    int lead = L - 1;
+    const char *vp = v ? reinterpret_cast<const char *>(v + pin + a.off_h) : nullptr;
+    const char *wp = w ? reinterpret_cast<const char *>(w + pin + a.off_g) : nullptr;
+    auto load_block = [&](int first, int avail, double (&nv)[R], double (&nw)[R]) {
+        if (!EDGE && avail >= R) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                nv[r] = v ? ldg_early(row_ptr(vp, d, first + r)) : 0.0;
+                nw[r] = w ? ldg_early(row_ptr(wp, d, first + r)) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const bool live = r < avail;
+                if (EDGE) {
+                    const long long pos = pin + (long long)(first + r) * a.d;
+                    nv[r] = (live && v) ? ext_load<true>(v, pos + a.off_h, a.n_in, a.mode) : 0.0;
+                    nw[r] = (live && w) ? ext_load<true>(w, pos + a.off_g, a.n_in, a.mode) : 0.0;
+                } else {
+                    nv[r] = (live && v) ? __ldg(row_ptr(vp, d, first + r)) : 0.0;
+                    nw[r] = (live && w) ? __ldg(row_ptr(wp, d, first + r)) : 0.0;
+                }
+            }
+        }
+    };
+    double nv[R], nw[R];
+    load_block(0, in_left, nv, nw);
+    while (in_left > 0) {
+        double cv[R], cw[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { cv[r] = nv[r]; cw[r] = THR ? (thr_nonneg ? vw_threshold_nonneg(nw[r], lam, a.thr_soft) : vw_threshold_value(nw[r], lam, a.thr_soft)) : nw[r]; }
+        if (in_left > R) load_block(R, in_left - R, nv, nw);
+        double o[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double aa = cv[r], bb = cw[r];
+#pragma unroll
+            for (int k = K - 2; k >= 0; k--) {
+                const double an = fma(-c.t[k], bb, aa);
+                bb = fma(c.t[k], aa, bb);
+                aa = dl[k][r & 1];
+                dl[k][r & 1] = an;
+            }
+            const double y0 = fma(c.b[2], bb, c.b[0] * aa);
+            const double y1 = fma(c.b[3], bb, c.b[1] * aa);
+            o[r] = y0prev + y1;
+            y0prev = y0;
+        }
+        if (lead <= 0 && in_left >= R) {
+#pragma unroll
+            for (int j = 0; j < R; j++) *row_ptr(op, d, j) = o[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j++)
+                if (j >= lead && j < in_left) *row_ptr(op, d, j) = o[j];
+        }
+        const long long step = (long long)d * (8 * R);
+        if (!EDGE) { if (vp) vp += step; if (wp) wp += step; }
+        pin += (long long)R * a.d;
+        op += step;
+        in_left -= R;
+        lead -= R;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCThreads, 3) k_column_synthesis_lat(const __grid_constant__ ColArgs a, const __grid_constant__ ColLat c) {
+    constexpr int L = 2 * K;
+    const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
+    const int d = (int)a.d;
+    const long long chunk = gid / a.d;
+    const int col = (int)(gid - chunk * a.d);
+    if (chunk >= a.chunks) return;
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const double *v = a.x ? a.x + b * a.ldx : nullptr;
+        const double *w = a.w_in ? a.w_in + b * a.ldw_in : nullptr;
+        const long long rows = (a.n_out - col + a.d - 1) / a.d;
+        const long long o_start = chunk * a.rows_per_chunk;
+        const long long left64 = rows - o_start;
+        if (left64 <= 0) continue;
+        const int nout = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const long long pin0 = a.t0 + col + o_start * a.d;
+        char *op = reinterpret_cast<char *>(a.v + b * a.ldv + col + o_start * a.d) - (long long)d * (8 * (L - 1));
+        const long long lo_off = a.off_h < a.off_g ? a.off_h : a.off_g, hi_off = a.off_h < a.off_g ? a.off_g : a.off_h;
+        const long long last_pos = pin0 + (long long)(nout + L - 2) * a.d;
+        const bool thr_on = a.thr != nullptr && w != nullptr;
+        const double lam = thr_on ? a.thr[a.thr_per_row ? b : 0] : 0.0;
+        const bool inside = pin0 + lo_off >= 0 && last_pos + hi_off < a.n_in;
+        if (thr_on) {
+            if (inside) col_synth_chunk_lat<K, false, true>(a, c, v, w, op, d, nout, pin0, lam);
+            else col_synth_chunk_lat<K, true, true>(a, c, v, w, op, d, nout, pin0, lam);
+        } else {
+            if (inside) col_synth_chunk_lat<K, false, false>(a, c, v, w, op, d, nout, pin0, lam);
+            else col_synth_chunk_lat<K, true, false>(a, c, v, w, op, d, nout, pin0, lam);
+        }
+    }
+}
+
+// the lattice builds exist for the lengths whose direct column kernels are FP64-bound
+bool lattice_for(const vw_ctx *ctx, const VwFilt32 &f, int l, bool qmf, ColLat &c) {
+    if (!ctx->opt_lattice || !qmf || l != 30) return false;
+    VwLattice lat;
+    vw_lattice_fit(f.h, f.g, l, lat);
+    if (!lat.ok) return false;
+    for (int j = 0; j < 4; j++) c.b[j] = lat.b[j];
+    for (int j = 0; j < VW_LATTICE_MAX_K - 1; j++) c.t[j] = j < lat.k - 1 ? lat.t[j] : 0.0;
+    return true;
+}
+
 // short filters keep both tap arrays in uniform registers; from 12 taps on a quadrature-mirror pair takes the QMF build
 #define VW_DISPATCH_CL(L, Q, CALL)                                  \
     switch (L) {                                                    \
@@ -340,7 +566,7 @@ __global__ void __launch_bounds__(kCThreads, (L >= 24) ? VW_COL_CS : ((L >= 16) 
 // waves: with 2-3 resident CTAs per SM a naturally sized grid of ~1800 CTAs ran 4.1 or 6.15 waves, i.e. 12-18 % of the
 // run with most SMs idle (and 2.05 waves -> 68 % at the 2^25-sample spans of an 8-GPU job).
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per_sm, dim3 &grid, int &rows_per_chunk,
-             int &chunks_out) {
+             int &chunks_out, int64_t gran = kCR) {
     if (d < 1 || d > (1ll << 30)) return VW_EUNSUPPORTED;
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
@@ -350,7 +576,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
     if (chunks < 1) chunks = 1;
     int64_t rpc = (rows + chunks - 1) / chunks;
     if (rpc < 4 * kCR) rpc = 4 * kCR;
-    rpc = ((rpc + kCR - 1) / kCR) * kCR;
+    rpc = ((rpc + gran - 1) / gran) * gran;
     chunks = (rows + rpc - 1) / rpc;
     int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;
     const int64_t by = batch < 65535 ? batch : 65535;
@@ -361,7 +587,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
         const int64_t target = std::max<int64_t>(1, waves * resident / by);            // blocks along x
         int64_t c2 = std::max<int64_t>(1, target * kCThreads / d);                      // chunks that fit the target
         int64_t r2 = (rows + c2 - 1) / c2;
-        r2 = ((r2 + kCR - 1) / kCR) * kCR;
+        r2 = ((r2 + gran - 1) / gran) * gran;
         c2 = (rows + r2 - 1) / r2;
         const int64_t b2 = (c2 * d + kCThreads - 1) / kCThreads;
         if (b2 <= blocks && r2 < (1ll << 30)) { rpc = r2; chunks = c2; blocks = b2; }
@@ -397,6 +623,14 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
     for (int k = 0; k < VW_FUSED_MAX_L; k++) { a.f.h[k] = k < l ? f.h[k] : 0.0; a.f.g[k] = k < l ? f.g[k] : 0.0; }
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);
     int per_sm = 0;
+    ColLat lat;
+    if (lattice_for(ctx, a.f, l, qmf, lat)) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat<15>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR)) return rc;
+        k_column_analysis_lat<15><<<grid, kCThreads, 0, ctx->stream>>>(a, lat);
+        ctx->launches++;
+        return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice) launch");
+    }
 #define VW_CO(LL, QQ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis<LL, QQ>, kCThreads, 0)
     VW_DISPATCH_CL(l, qmf, VW_CO)
 #undef VW_CO
@@ -428,6 +662,14 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
     }
     const bool qmf = vw_is_qmf(a.f.h, a.f.g, l);   // on the arrays as the kernel sees them (sigma = -1 streams are reversed)
     int per_sm = 0;
+    ColLat lat;
+    if (lattice_for(ctx, a.f, l, qmf, lat)) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat<15>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR)) return rc;
+        k_column_synthesis_lat<15><<<grid, kCThreads, 0, ctx->stream>>>(a, lat);
+        ctx->launches++;
+        return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (lattice) launch");
+    }
 #define VW_CO(LL, QQ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis<LL, QQ>, kCThreads, 0)
     VW_DISPATCH_CL(l, qmf, VW_CO)
 #undef VW_CO

@@ -45,6 +45,20 @@ inline bool vw_is_qmf(const double *h, const double *g, int l) {
 }
 struct VwPlanGroup { int first, nlev; int64_t tile; double cost; };
 
+// Paraunitary lattice of a quadrature-mirror pair (vw_lattice.cu): E(z) = S_{k-1} Lam ... S_1 Lam B with
+// S_j = [[1, t_j], [-t_j, 1]] and B = [[b0, b1], [b2, b3]] (carries the scale).  ok: the double-rounded parameters
+// reproduce every tap of h and g to VW_LATTICE_TOL, so the lattice kernels may stand in for the direct form.
+#define VW_LATTICE_MAX_K (VW_FUSED_MAX_L / 2)
+#define VW_LATTICE_TOL 2.0e-16
+struct VwLattice {
+    int k = 0;
+    bool ok = false;
+    double tap_err = 0.0;
+    double t[VW_LATTICE_MAX_K - 1] = {};
+    double b[4] = {};
+};
+void vw_lattice_fit(const double *h, const double *g, int l, VwLattice &out);
+
 struct vw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -93,6 +107,7 @@ struct vw_ctx {
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)
+    int64_t opt_lattice = 1; // column kernels of long quadrature-mirror pairs (>= 24 taps) in lattice form when the taps fit one (vw_lattice.cu)
 };
 
 // MutableMultiLevelMODWTResult.applyThresholdToArray (CORE/modwt/MutableMultiLevelMODWTResult.java:97-118):
