@@ -131,20 +131,22 @@ def eng():
         e.set_option(k, v)
 
 
-def _both(eng, fn):
-    """fn() with the lattice kernels and with the direct-form kernels"""
-    eng.set_option("lattice", 1)
+def _both(eng, fn, lattice=3):
+    """fn() with the lattice kernels (3: two levels per pass where the plan pairs them, 1: one level per pass) and with
+    the direct-form kernels"""
+    eng.set_option("lattice", lattice)
     a = fn()
     eng.set_option("lattice", 0)
     b = fn()
-    eng.set_option("lattice", 1)
+    eng.set_option("lattice", 3)
     return a, b
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lattice", [3, 1])
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("b,n,levels", [(1, 65536, 8), (3, 40001, 7), (2, 9000, 5), (1, 1 << 20, 10)])
-def test_coif5_column_levels_in_lattice_form_against_the_oracle(eng, mode, b, n, levels):
+@pytest.mark.parametrize("b,n,levels", [(1, 65536, 8), (3, 40001, 7), (2, 9000, 5), (1, 1 << 20, 10), (2, 3001, 5), (1, 12346, 6)])
+def test_coif5_column_levels_in_lattice_form_against_the_oracle(eng, mode, b, n, levels, lattice):
     import vectorwave_b200 as vw
     from vectorwave_b200.modwt import multilevel_alignment
     h, g, wid = filters("coif5")
@@ -153,7 +155,7 @@ def test_coif5_column_levels_in_lattice_form_against_the_oracle(eng, mode, b, n,
     bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
     align, order = multilevel_alignment(vw.get_wavelet("coif5"), bm, levels)
     l0 = eng.launch_count()
-    (w, v), (wd, vd) = _both(eng, lambda: eng.forward(x, hs, gs, levels, mode))
+    (w, v), (wd, vd) = _both(eng, lambda: eng.forward(x, hs, gs, levels, mode), lattice)
     assert eng.launch_count() > l0
     w, v, wd, vd = (np.asarray(a) for a in (w, v, wd, vd))
     t = REL * float(np.max(np.abs(x)))
@@ -163,7 +165,7 @@ def test_coif5_column_levels_in_lattice_form_against_the_oracle(eng, mode, b, n,
         assert float(np.max(np.abs(w[:, i, :] - wo))) <= t
         assert float(np.max(np.abs(v[i] - vo))) <= t
         ref = cref.reconstruct(wo, vo, h, g, mode, wid)
-        xr, xrd = _both(eng, lambda: np.asarray(eng.inverse(wo[:, None, :].copy(), vo[None, :].copy(), hs, gs, mode, align, order)))
+        xr, xrd = _both(eng, lambda: np.asarray(eng.inverse(wo[:, None, :].copy(), vo[None, :].copy(), hs, gs, mode, align, order)), lattice)
         tr = REL * max(float(np.max(np.abs(ref))), float(np.max(np.abs(x))))
         assert float(np.max(np.abs(xr[0] - ref))) <= tr
         assert float(np.max(np.abs(xrd[0] - ref))) <= tr
@@ -188,7 +190,24 @@ def test_lattice_is_what_runs_for_coif5_and_only_for_it(eng):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [1, 2])
+def test_pairs_save_launches_and_singles_take_over_where_pairs_do_not_apply(eng):
+    """PERIODIC: levels 3-8 of coif5 run as three pair launches; SYMMETRIC keeps one level per launch (V_j is re-mirrored
+    per level, which the in-register cascade cannot do); lattice = 1 switches the pairs off."""
+    h, g, _ = filters("coif5")
+    x = np.random.default_rng(8).standard_normal((1, 1 << 16))
+    counts = {}
+    for key, lat, mode in (("pairs", 3, 0), ("singles", 1, 0), ("symmetric", 3, 2)):
+        eng.set_option("lattice", lat)
+        eng.forward(x, h * S, g * S, 8, mode)          # plan + lattice fit cached
+        l0 = eng.launch_count()
+        eng.forward(x, h * S, g * S, 8, mode)
+        counts[key] = eng.launch_count() - l0
+    eng.set_option("lattice", 3)
+    assert counts["singles"] - counts["pairs"] == 3 and counts["symmetric"] == counts["singles"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_coif5_swt_denoise_thresholds_on_load_in_the_lattice_synthesis(eng, mode):
     import vectorwave_b200 as vw
     from vectorwave_b200.modwt import multilevel_alignment

@@ -535,9 +535,253 @@ __global__ void __launch_bounds__(kCThreads, 3) k_column_synthesis_lat(const __g
     }
 }
 
+// ---- two levels per pass ------------------------------------------------------------------------------------------
+// With the lattice the column kernels stream at the HBM roof, so the next lever is bytes.  Level j+1 at dilation 2d is,
+// inside one level-j column (rows q <-> positions col + q d), a filter over every SECOND row: the even rows are the
+// level-(j+1) column col, the odd rows the column col + d.  And the level-j lattice itself only chains rows of equal parity
+// (its delays are two rows); the parities meet in the 2 x 2 base product alone.  So a PAIR of lanes takes one level-j column
+// -- the even lane its even rows, the odd lane the odd rows -- and each lane runs level j on its own rows (delay lines one
+// slot deep), then level j+1 on the V_j it has just produced (two slots), everything in registers; the one value per row
+// that crosses parities (analysis: the neighbouring input row; synthesis: the second output channel) moves by a lane
+// shuffle.  V_j never exists in memory: the analysis reads V_{j-1} and writes W_j, W_{j+1}, V_{j+1} (32 B per sample for two
+// levels instead of 48), the synthesis reads V_{j+1}, W_{j+1}, W_j and writes V_{j-1}.  State per lane: 3 (K-1) + 2 doubles.
+// Valid where V_j outside the row is what the cascade computes from the extended input: PERIODIC, ZERO_PADDING, span calls --
+// not SYMMETRIC (V_j is re-mirrored per level, ScalarOps.java:818-835), which keeps one level per pass.
+struct ColPair {
+    const double *x; long long ldx;       // analysis: V_{j-1};  synthesis: V_{j+1}
+    const double *wa; long long ldwa;     // synthesis: W_{j+1}
+    const double *wb; long long ldwb;     // synthesis: W_j
+    double *o0; long long ldo0;           // analysis: V_{j+1};  synthesis: V_{j-1}
+    double *o1; long long ldo1;           // analysis: W_j
+    double *o2; long long ldo2;           // analysis: W_{j+1}
+    long long n_in, t0, n_out, batch, d;  // d = dilation of level j; a lane walks positions c2 + i * 2d, c2 in [0, 2d)
+    int rows_per_chunk, chunks, mode;     // rows = a lane's own rows (level-(j+1) rows)
+    const double *thr; int thr_per_row, thr_soft;
+    ColLat c;
+};
+
+#ifndef VW_PAIR_CTAS
+#define VW_PAIR_CTAS 2
+#endif
+constexpr int kPR = 8;    // own rows per block (even: the level-(j+1) delay slots are compile-time registers)
+
+__device__ __forceinline__ double shfl_partner(unsigned mask, double v) {
+    return __shfl_xor_sync(mask, v, 1);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat2(const __grid_constant__ ColPair a) {
+    constexpr int L = 2 * K, R = kPR;
+    // V_{j+1} at own row i needs V_j at own rows i-(L-1) .. i, each of which needs L-1 level-j rows = L/2 own rows more
+    constexpr int LEAD = ((L - 1 + L / 2 + R - 1) / R) * R;
+    static_assert(R % 2 == 0 && LEAD % 2 == 0, "delay slots must be compile-time registers");
+    const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
+    const int d = (int)a.d;
+    const long long d2 = 2 * a.d;
+    const long long pid = gid >> 1;            // lane pair = one level-j column of one chunk
+    const int rho = (int)(gid & 1);            // this lane's row parity inside the level-j column
+    const long long chunk = pid / a.d;
+    const long long c2 = (pid - chunk * a.d) + (rho ? a.d : 0);   // own level-(j+1) column
+    const unsigned mask = __ballot_sync(0xffffffffu, chunk < a.chunks);
+    if (chunk >= a.chunks) return;
+    const ColLat &c = a.c;
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const long long rows = a.n_out > c2 ? (a.n_out - c2 + d2 - 1) / d2 : 0;   // own rows inside the output range
+        const long long i0 = chunk * a.rows_per_chunk;
+        long long left64 = rows - i0;
+        if (left64 < 0) left64 = 0;
+        const int left = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const int steps = __reduce_max_sync(mask, left) + LEAD;        // the lanes of a warp walk in step (shuffles)
+        const long long p = a.t0 + c2 + i0 * d2;                       // position of the first own output row
+        const long long p_lead = p - (long long)LEAD * d2;
+        const double *x = a.x + b * a.ldx;
+        const long long step = d2 * (8 * R);
+        const long long back = d2 * (8 * LEAD);
+        const char *xp = reinterpret_cast<const char *>(x + p) - back;               // own row 0 of the CURRENT block
+        char *vp = reinterpret_cast<char *>(a.o0 + b * a.ldo0 + (p - a.t0)) - back;
+        char *w1p = reinterpret_cast<char *>(a.o1 + b * a.ldo1 + (p - a.t0)) - back;
+        char *w2p = reinterpret_cast<char *>(a.o2 + b * a.ldo2 + (p - a.t0)) - back;
+        const int d2i = (int)d2;
+        double dl1[K - 1], dl2[K - 1][2];
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
+        double xprev = 0.0, vprev = 0.0;
+        const int have = LEAD + left;          // own rows that exist from step 0 on (warm-up + outputs)
+        // generic load of own row s (counted from the first warm-up row)
+        auto ld = [&](int s) -> double {
+            if (s >= have) return 0.0;
+            const long long pos = p_lead + (long long)s * d2;
+            return (pos >= 0 && pos < a.n_in) ? __ldg(x + pos) : ext_load<true>(x, pos, a.n_in, a.mode);
+        };
+        double buf[R];      // the current block's own rows; each is replaced by the next block's row once consumed
+#pragma unroll
+        for (int r = 0; r < R; r++) buf[r] = ld(r);
+        auto row = [&](int r, double xv, double &w1, double &v2, double &w2) {
+            // the neighbouring level-j row: the even lane needs the odd lane's PREVIOUS row, the odd lane the even lane's current one
+            const double un = shfl_partner(mask, rho ? xprev : xv);
+            xprev = xv;
+            double aa = fma(c.b[1], un, c.b[0] * xv);
+            double bb = fma(c.b[3], un, c.b[2] * xv);
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) {
+                const double bd = dl1[k];
+                dl1[k] = bb;
+                const double an = fma(c.t[k], bd, aa);
+                bb = fma(-c.t[k], aa, bd);
+                aa = an;
+            }
+            w1 = bb;
+            double a2 = fma(c.b[1], vprev, c.b[0] * aa);
+            double b2 = fma(c.b[3], vprev, c.b[2] * aa);
+            vprev = aa;
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) {
+                const double bd = dl2[k][r & 1];
+                dl2[k][r & 1] = b2;
+                const double an = fma(c.t[k], bd, a2);
+                b2 = fma(-c.t[k], a2, bd);
+                a2 = an;
+            }
+            v2 = a2; w2 = b2;
+        };
+        for (int s0 = 0; s0 < steps; s0 += R) {
+            // steady state for the whole warp: every lane stores this whole block and prefetches a whole block inside the row
+            const bool fast = s0 >= LEAD && s0 + 2 * R <= have;
+            if (__all_sync(mask, fast)) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double xv = buf[r];
+                    buf[r] = ldg_early(row_ptr(xp, d2i, R + r));
+                    double w1, v2, w2;
+                    row(r, xv, w1, v2, w2);
+                    *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double xv = buf[r];
+                    buf[r] = ld(s0 + R + r);
+                    double w1, v2, w2;
+                    row(r, xv, w1, v2, w2);
+                    if (s0 + r >= LEAD && s0 + r < have) { *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2; }
+                }
+            }
+            xp += step; vp += step; w1p += step; w2p += step;
+        }
+    }
+}
+
+// Synthesis pair.  A lane consumes (V_{j+1}, W_{j+1}) at own row s, which completes V_j at own row s - (L-1); that value and
+// W_j of the same row go through the level-j cascade, whose two output channels belong to neighbouring level-j rows:
+// V_{j-1}[q] = y0(q + L-2) + y1(q + L-1) -- one term from each lane of the pair (ScalarOps / MultiLevelMODWTTransform.java:554-601
+// index rule t + k d).  The even lane's output lags its consumed row by L-1 + K-1 own rows, the odd lane's by one more.
+template <int K, bool THR>
+__global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_lat2(const __grid_constant__ ColPair a) {
+    constexpr int L = 2 * K, R = kPR;
+    constexpr int LAG1 = L - 1;            // own rows between a consumed (V, W)_{j+1} row and the V_j row it completes
+    static_assert(R % 2 == 0, "delay slots must be compile-time registers");
+    const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
+    const long long d2 = 2 * a.d;
+    const int d2i = (int)d2;
+    const long long pid = gid >> 1;
+    const int rho = (int)(gid & 1);
+    const long long chunk = pid / a.d;
+    const long long c2 = (pid - chunk * a.d) + (rho ? a.d : 0);
+    const unsigned mask = __ballot_sync(0xffffffffu, chunk < a.chunks);
+    if (chunk >= a.chunks) return;
+    const ColLat &c = a.c;
+    const int lag = LAG1 + (K - 1) + rho;     // own rows between a consumed row and the output row it completes
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const double *v2 = a.x + b * a.ldx;
+        const double *w2 = a.wa + b * a.ldwa;
+        const double *w1 = a.wb + b * a.ldwb;
+        const long long rows = a.n_out > c2 ? (a.n_out - c2 + d2 - 1) / d2 : 0;
+        const long long i0 = chunk * a.rows_per_chunk;
+        long long left64 = rows - i0;
+        if (left64 < 0) left64 = 0;
+        const int nout = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const int steps = __reduce_max_sync(mask, nout + lag);     // consumed own rows: the warp walks in step
+        const long long pin0 = a.t0 + c2 + i0 * d2;                // position of consumed own row 0
+        const bool inside = pin0 + (long long)(steps + R) * d2 < a.n_in;   // every row this lane may touch lies inside the row
+        const double lam = THR ? a.thr[a.thr_per_row ? b : 0] : 0.0;
+        const bool thr_nonneg = !(lam < 0.0);
+        auto thr = [&](double v) { return THR ? (thr_nonneg ? vw_threshold_nonneg(v, lam, a.thr_soft) : vw_threshold_value(v, lam, a.thr_soft)) : v; };
+        auto ld2 = [&](const double *rowp, int s) -> double {
+            if (s >= steps) return 0.0;
+            const long long pos = pin0 + (long long)s * d2;
+            return pos < a.n_in ? __ldg(rowp + pos) : ext_load<true>(rowp, pos, a.n_in, a.mode);
+        };
+        auto ld1 = [&](int s) -> double { return s < LAG1 ? 0.0 : ld2(w1, s - LAG1); };
+        const long long step = d2 * (8 * R);
+        const char *v2p = reinterpret_cast<const char *>(v2 + pin0);                 // consumed own row 0 of the CURRENT block
+        const char *w2p = reinterpret_cast<const char *>(w2 + pin0);
+        const char *w1p = reinterpret_cast<const char *>(w1 + pin0) - d2 * (8 * LAG1);
+        char *op = reinterpret_cast<char *>(a.o0 + b * a.ldo0 + c2 + i0 * d2) - d2 * (8 * (long long)lag);
+        double dl1[K - 1], dl2[K - 1][2];
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
+        double y0prev = 0.0, z0prev = 0.0;
+        double bv[R], bw2[R], bw1[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { bv[r] = ld2(v2, r); bw2[r] = ld2(w2, r); bw1[r] = ld1(r); }
+        auto row = [&](int r, double cv, double cw2, double cw1) -> double {
+            double aa = cv, bb = cw2;
+#pragma unroll
+            for (int k = K - 2; k >= 0; k--) {
+                const double an = fma(-c.t[k], bb, aa);
+                bb = fma(c.t[k], aa, bb);
+                aa = dl2[k][r & 1];
+                dl2[k][r & 1] = an;
+            }
+            const double y0 = fma(c.b[2], bb, c.b[0] * aa);
+            const double y1 = fma(c.b[3], bb, c.b[1] * aa);
+            aa = y0prev + y1;               // V_j at own row s - (L-1)
+            y0prev = y0;
+            bb = cw1;
+#pragma unroll
+            for (int k = K - 2; k >= 0; k--) {
+                const double an = fma(-c.t[k], bb, aa);
+                bb = fma(c.t[k], aa, bb);
+                aa = dl1[k];
+                dl1[k] = an;
+            }
+            const double z0 = fma(c.b[2], bb, c.b[0] * aa);
+            const double z1 = fma(c.b[3], bb, c.b[1] * aa);
+            const double z1n = shfl_partner(mask, z1);
+            const double out = (rho ? z0prev : z0) + z1n;
+            z0prev = z0;
+            return out;
+        };
+        for (int s0 = 0; s0 < steps; s0 += R) {
+            const bool fast = inside && s0 >= lag && s0 + R <= nout + lag && s0 + 2 * R <= steps;
+            if (__all_sync(mask, fast)) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double cv = bv[r], cw2 = thr(bw2[r]), cw1 = thr(bw1[r]);
+                    bv[r] = ldg_early(row_ptr(v2p, d2i, R + r));
+                    bw2[r] = ldg_early(row_ptr(w2p, d2i, R + r));
+                    bw1[r] = ldg_early(row_ptr(w1p, d2i, R + r));
+                    *row_ptr(op, d2i, r) = row(r, cv, cw2, cw1);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double cv = bv[r], cw2 = thr(bw2[r]), cw1 = thr(bw1[r]);
+                    bv[r] = ld2(v2, s0 + R + r);
+                    bw2[r] = ld2(w2, s0 + R + r);
+                    bw1[r] = ld1(s0 + R + r);
+                    const double o = row(r, cv, cw2, cw1);
+                    if (s0 + r >= lag && s0 + r < nout + lag) *row_ptr(op, d2i, r) = o;
+                }
+            }
+            v2p += step; w2p += step; w1p += step; op += step;
+        }
+    }
+}
+
 // the lattice builds exist for the lengths whose direct column kernels are FP64-bound
 bool lattice_for(const vw_ctx *ctx, const VwFilt32 &f, int l, bool qmf, ColLat &c) {
-    if (!ctx->opt_lattice || !qmf || l != 30) return false;
+    if (!(ctx->opt_lattice & 1) || !qmf || l != 30) return false;
     VwLattice lat;
     vw_lattice_fit(f.h, f.g, l, lat);
     if (!lat.ok) return false;
@@ -566,12 +810,12 @@ bool lattice_for(const vw_ctx *ctx, const VwFilt32 &f, int l, bool qmf, ColLat &
 // waves: with 2-3 resident CTAs per SM a naturally sized grid of ~1800 CTAs ran 4.1 or 6.15 waves, i.e. 12-18 % of the
 // run with most SMs idle (and 2.05 waves -> 68 % at the 2^25-sample spans of an 8-GPU job).
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per_sm, dim3 &grid, int &rows_per_chunk,
-             int &chunks_out, int64_t gran = kCR) {
+             int &chunks_out, int64_t gran = kCR, int64_t want_mul = 6) {
     if (d < 1 || d > (1ll << 30)) return VW_EUNSUPPORTED;
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
     // L-1 warm-up rows each chunk re-reads
-    const int64_t want_threads = (int64_t)ctx->sm_count * 512 * 6;
+    const int64_t want_threads = (int64_t)ctx->sm_count * 512 * want_mul;
     int64_t chunks = (want_threads + d * batch - 1) / (d * batch);
     if (chunks < 1) chunks = 1;
     int64_t rpc = (rows + chunks - 1) / chunks;
@@ -600,6 +844,59 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
 }
 
 }  // namespace
+
+// Levels j and j+1 (d = dilation of level j) in one pass; VW_EUNSUPPORTED when the pair form does not apply (the caller
+// then runs the two levels one by one).
+static bool pair_ok(const vw_ctx *ctx, const VwFilt &f, int l, int64_t d, int mode, ColLat &c) {
+    if (!(ctx->opt_lattice & 2) || mode == VW_SYMMETRIC || d < 1 || d > (1ll << 28)) return false;
+    VwFilt32 f32;
+    if (l > VW_FUSED_MAX_L) return false;
+    for (int k = 0; k < VW_FUSED_MAX_L; k++) { f32.h[k] = k < l ? f.h[k] : 0.0; f32.g[k] = k < l ? f.g[k] : 0.0; }
+    return lattice_for(ctx, f32, l, vw_is_qmf(f32.h, f32.g, l), c);
+}
+
+int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, int64_t ldw1, double *w2, int64_t ldw2, double *v2,
+                        int64_t ldv2, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d,
+                        int mode) {
+    ColPair a;
+    if (n_out < 1 || batch < 1 || !pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+    a.x = x; a.ldx = ldx; a.wa = a.wb = nullptr; a.ldwa = a.ldwb = 0;
+    a.o0 = v2; a.ldo0 = ldv2; a.o1 = w1; a.ldo1 = ldw1; a.o2 = w2; a.ldo2 = ldw2;
+    a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.mode = mode;
+    a.thr = nullptr; a.thr_per_row = 0; a.thr_soft = 0;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat2<15>, kCThreads, 0);
+    dim3 grid;
+    // fewer, longer chunks than the single-level kernels: every chunk re-reads 3 (L-1) warm-up rows
+    if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+    k_column_analysis_lat2<15><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice pair) launch");
+}
+
+int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const double *w2, int64_t ldw2, const double *w1,
+                         int64_t ldw1, double *out, int64_t ldo, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch,
+                         const VwFilt &f, int l, int64_t d, int mode, const double *thr_dev, int thr_per_row, int thr_soft) {
+    ColPair a;
+    if (n_out < 1 || batch < 1 || !v2 || !w2 || !w1 || !pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+    a.x = v2; a.ldx = ldv2; a.wa = w2; a.ldwa = ldw2; a.wb = w1; a.ldwb = ldw1;
+    a.o0 = out; a.ldo0 = ldo; a.o1 = a.o2 = nullptr; a.ldo1 = a.ldo2 = 0;
+    a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.mode = mode;
+    a.thr = thr_dev; a.thr_per_row = thr_per_row; a.thr_soft = thr_soft;
+    int per_sm = 0;
+    dim3 grid;
+    if (thr_dev) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, true>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+        k_column_synthesis_lat2<15, true><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, false>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+        k_column_synthesis_lat2<15, false><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (lattice pair) launch");
+}
 
 int vw_column_min_level(const vw_ctx *ctx, int l, bool forward) {
     if (ctx->opt_colmin > 0) return (int)ctx->opt_colmin;

@@ -830,9 +830,17 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
     best[0] = 0.0;
     for (int done = 0; done < levels; done++) {
         if (best[done] == INFINITY) continue;
-        for (int nf = 1; nf <= cap && done + nf <= levels; nf++) {
+        // two column levels per pass: the lattice pair kernels (vw_column.cu) exist for 30 taps; a pair the kernels decline at
+        // run time (a table that fits no lattice, SYMMETRIC) is run level by level by the cascade drivers
+        const bool pair_len = l == 30 && (ctx->opt_lattice & 2) && ctx->opt_poly != 0 && done + 1 >= vw_column_min_level(ctx, l, forward);
+        for (int nf = 1; nf <= std::max(cap, pair_len ? 2 : 1) && done + nf <= levels; nf++) {
             int64_t tile;
-            double c = group_cost(ctx, forward, l, done + 1, nf, n, &tile);
+            double c = nf <= cap ? group_cost(ctx, forward, l, done + 1, nf, n, &tile) : INFINITY;
+            if (nf > cap) tile = -1;
+            if (nf == 2 && pair_len && (int64_t)3 * (l - 1) * (1ll << done) <= n) {
+                const double cpair = std::max(2.0 * (l + 3) / 64.0 / 0.80, 32.0 / 22.5 / 0.80) + 0.1;   // two levels: 32 B/sample
+                if (cpair < c) { c = cpair; tile = -2; }
+            }
             if (nf == 1 && done + 1 >= vw_column_min_level(ctx, l, forward) && ctx->opt_poly != 0) {
                 // deep single level (dilation >= 32): the column kernel streams 24 B/sample with no halo recompute
                 bool has = l == 2 || l == 4 || l == 6 || l == 8 || l == 10 || l == 12 || l == 16 || l == 18 || l == 20 || l == 30;

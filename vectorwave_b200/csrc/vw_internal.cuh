@@ -107,7 +107,7 @@ struct vw_ctx {
     int64_t opt_tile = 0, opt_fuse = 0, opt_threads = 0, opt_poly = 1;
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)
-    int64_t opt_lattice = 1; // column kernels of long quadrature-mirror pairs (>= 24 taps) in lattice form when the taps fit one (vw_lattice.cu)
+    int64_t opt_lattice = 3; // column kernels of long quadrature-mirror pairs (>= 24 taps) in lattice form when the taps fit one (vw_lattice.cu): bit 0 = single levels, bit 1 = two levels per pass
 };
 
 // MutableMultiLevelMODWTResult.applyThresholdToArray (CORE/modwt/MutableMultiLevelMODWTResult.java:97-118):
@@ -223,6 +223,14 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
 int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double *w, int64_t ldw, double *out, int64_t ldo,
                         int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d, int mode,
                         vw_align al, const double *thr_dev = nullptr, int thr_per_row = 0, int thr_soft = 0);
+
+// levels j and j+1 in one pass (lattice pair kernels; d = dilation of level j).  VW_EUNSUPPORTED: run them one by one.
+int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, int64_t ldw1, double *w2, int64_t ldw2, double *v2,
+                        int64_t ldv2, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d,
+                        int mode);
+int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const double *w2, int64_t ldw2, const double *w1,
+                         int64_t ldw1, double *out, int64_t ldo, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch,
+                         const VwFilt &f, int l, int64_t d, int mode, const double *thr_dev, int thr_per_row, int thr_soft);
 
 // ---- exact order statistics (vw_select.cu) ---------------------------------------------------
 // median(|w1|) per row -> universal thresholds written to thr_dev[batch] (device).

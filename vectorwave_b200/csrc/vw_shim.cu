@@ -242,6 +242,13 @@ int forward_device(vw_ctx *ctx, const double *x, int64_t batch, int64_t n, int64
             rc = vw_fused_forward(ctx, p, f);
             if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
             if (rc == VW_OK) { cur = vout; ld_cur = ld_vout; pp ^= 1; }
+        } else if (allow_fused && g.tile == -2 && g.nlev == 2) {
+            // two column levels in one pass (lattice pair kernels): V of the first level never exists in memory
+            if ((rc = pick_out(g.first + 1, vout, ld_vout))) return rc;
+            rc = vw_column_analysis2(ctx, cur, ld_cur, w + (int64_t)(g.first - 1) * lsw, ldw, w + (int64_t)g.first * lsw, ldw, vout,
+                                     ld_vout, n, 0, n, batch, f, l, (int64_t)1 << (g.first - 1), mode);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            if (rc == VW_OK) { cur = vout; ld_cur = ld_vout; pp ^= 1; }
         }
         if (rc == VW_EUNSUPPORTED) {
             for (int level = g.first; level < g.first + g.nlev; level++) {
@@ -308,6 +315,12 @@ int inverse_device(vw_ctx *ctx, const double *w, int64_t ldw, int64_t lsw, const
                          (detail_mask >> (g.first - 1)) & ((g.nlev >= 64 ? ~0ull : ((1ull << g.nlev) - 1))),
                          out, ld_out, batch, n, n, l, g.first, g.nlev, mode, thr_dev, thr_per_row, thr_soft, g.tile};
             rc = vw_fused_inverse(ctx, p, f);
+            if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+            if (rc == VW_OK) { cur = out; ld_cur = ld_out; pp ^= 1; }
+        } else if (allow_fused && g.tile == -2 && g.nlev == 2 && cur && ((detail_mask >> (g.first - 1)) & 3ull) == 3ull) {
+            if ((rc = pick_out(g.first, out, ld_out))) return rc;
+            rc = vw_column_synthesis2(ctx, cur, ld_cur, w + (int64_t)g.first * lsw, ldw, w + (int64_t)(g.first - 1) * lsw, ldw, out,
+                                      ld_out, n, 0, n, batch, f, l, (int64_t)1 << (g.first - 1), mode, thr_dev, thr_per_row, thr_soft);
             if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
             if (rc == VW_OK) { cur = out; ld_cur = ld_out; pp ^= 1; }
         }
@@ -1114,7 +1127,12 @@ int vw_modwt_forward_span(vw_ctx *ctx, const double *vin, int64_t halo, int64_t 
     rc = VW_EUNSUPPORTED;
     // same kernel choice as the unsharded path: a single level at or above the column threshold runs on the column kernel
     const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0;
-    if (!exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
+    if (!exact && !(flags & VW_FLAG_NO_FUSE) && nlevels == 2 && first_level >= vw_column_min_level(ctx, l) && ctx->opt_poly != 0) {
+        rc = vw_column_analysis2(ctx, vin, 0, w, 0, w + level_stride_w, 0, vout, 0, n_in, halo, n_local, 1, f, l,
+                                 (int64_t)1 << (first_level - 1), VW_MODE_LINEAR);
+        if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+    }
+    if (rc == VW_EUNSUPPORTED && !exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
         VwFusedFwd p{vin, n_in, w, n_local, level_stride_w, vout, n_local, 1, n_in, halo, n_local,
                      l, first_level, nlevels, VW_MODE_LINEAR, 0};
         rc = vw_fused_forward(ctx, p, f);
@@ -1223,7 +1241,12 @@ int vw_modwt_inverse_span(vw_ctx *ctx, const double *vin, const double *w, int64
     const int64_t n_in = halo + n_local;
     rc = VW_EUNSUPPORTED;
     const bool column_first = nlevels == 1 && first_level >= vw_column_min_level(ctx, l, false) && ctx->opt_poly != 0;
-    if (!exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
+    if (!exact && !(flags & VW_FLAG_NO_FUSE) && nlevels == 2 && first_level >= vw_column_min_level(ctx, l, false) && ctx->opt_poly != 0) {
+        rc = vw_column_synthesis2(ctx, vin, 0, w + level_stride_w, 0, w, 0, vout, 0, n_in, 0, n_local, 1, f, l,
+                                  (int64_t)1 << (first_level - 1), VW_MODE_LINEAR, nullptr, 0, 0);
+        if (rc != VW_OK && rc != VW_EUNSUPPORTED) return rc;
+    }
+    if (rc == VW_EUNSUPPORTED && !exact && !(flags & VW_FLAG_NO_FUSE) && !column_first) {
         VwFusedInv p{vin, n_in, w, n_in, level_stride_w, nlevels >= 64 ? ~0ull : ((1ull << nlevels) - 1), vout, n_local,
                      1, n_in, n_local, l, first_level, nlevels, VW_MODE_LINEAR, nullptr, 0, 0, 0};
         rc = vw_fused_inverse(ctx, p, f);
