@@ -107,7 +107,7 @@ if __name__ == "__main__":
     ap.add_argument("--l2pf", type=int, default=3)
     ap.add_argument("--lean", type=int, default=3)
     ap.add_argument("--lean_small", type=int, default=1)
-    ap.add_argument("--lattice", type=int, default=1)
+    ap.add_argument("--lattice", type=int, default=3)
     a = ap.parse_args()
     for c in a.configs.split(","):
         run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin, "wave": a.wave, "l2pf": a.l2pf, "lean": a.lean, "lean_small": a.lean_small, "lattice": a.lattice}, a.mode, bool(a.denoise))

@@ -563,7 +563,13 @@ struct ColPair {
 #ifndef VW_PAIR_CTAS
 #define VW_PAIR_CTAS 2
 #endif
-constexpr int kPR = 8;    // own rows per block (even: the level-(j+1) delay slots are compile-time registers)
+#ifndef VW_PAIR_R
+#define VW_PAIR_R 8
+#endif
+// Measured on config #4 (tools/gpu_r2_pairab.sh): 2 CTAs/SM at ~250 registers beat 3 CTAs/SM with spills (forward 10.1 vs
+// 10.7 ms, inverse 10.4 vs 13.5), 8 rows per block beat 4, and a prefetch.global.L2 32 / 64 rows ahead of the register
+// prefetch changed nothing that survives a repeat (forward -2 %, inverse +5 %) -- not kept.
+constexpr int kPR = VW_PAIR_R;    // own rows per block (even: the level-(j+1) delay slots are compile-time registers)
 
 __device__ __forceinline__ double shfl_partner(unsigned mask, double v) {
     return __shfl_xor_sync(mask, v, 1);
