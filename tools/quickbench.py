@@ -19,6 +19,7 @@ CONFIGS = {
     "c2_db4_j2": ("db4", 4096, 4096, 2),
     "c3_sym8": ("sym8", 1024, 65536, 8),
     "c4_coif5": ("coif5", 1, 1 << 28, 10),
+    "c4e_coif5": ("coif5", 1, 1 << 25, 10),      # the span one rank of an 8-GPU job owns
     "c4_haar": ("haar", 1, 1 << 28, 10),
     "c4_db4": ("db4", 1, 1 << 28, 10),
     "c4_sym8": ("sym8", 1, 1 << 28, 10),
@@ -108,6 +109,7 @@ if __name__ == "__main__":
     ap.add_argument("--lean", type=int, default=3)
     ap.add_argument("--lean_small", type=int, default=1)
     ap.add_argument("--lattice", type=int, default=3)
+    ap.add_argument("--colrpc", type=int, default=0)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin, "wave": a.wave, "l2pf": a.l2pf, "lean": a.lean, "lean_small": a.lean_small, "lattice": a.lattice}, a.mode, bool(a.denoise))
+        run(c, a.reps, {"tile": a.tile, "fuse": a.fuse, "threads": a.threads, "poly": a.poly, "colmin": a.colmin, "wave": a.wave, "l2pf": a.l2pf, "lean": a.lean, "lean_small": a.lean_small, "lattice": a.lattice, "colrpc": a.colrpc}, a.mode, bool(a.denoise))

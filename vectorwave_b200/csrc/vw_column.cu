@@ -40,7 +40,13 @@ __device__ __forceinline__ void lds_tap_pair(uint32_t addr, double &h, double &g
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(h), "=d"(g) : "r"(addr));
 }
 
-__device__ __forceinline__ int64_t wrap_mod(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
+// one wrap is the common case (halo shorter than the row): a 64-bit % is a ~100-instruction call
+__device__ __forceinline__ int64_t wrap_mod(int64_t i, int64_t n) {
+    if (i >= n && i < 2 * n) return i - n;
+    if (i < 0 && i >= -n) return i + n;
+    i %= n;
+    return i < 0 ? i + n : i;
+}
 // EDGE == false: the caller has proven pos is inside [0, n) (interior chunks, the overwhelming majority)
 template <bool EDGE>
 __device__ __forceinline__ double ext_load(const double *__restrict__ row, int64_t pos, int64_t n, int mode) {
@@ -593,10 +599,14 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
     const ColLat &c = a.c;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const long long rows = a.n_out > c2 ? (a.n_out - c2 + d2 - 1) / d2 : 0;   // own rows inside the output range
-        const long long i0 = chunk * a.rows_per_chunk;
-        long long left64 = rows - i0;
+        // chunk boundaries spread evenly over the longest column (multiples of 8 rows): a short last chunk would keep its warp
+        // -- and with one wave per launch the whole kernel -- on the slow path long after the others have finished
+        const long long rows_max = (a.n_out + d2 - 1) / d2;
+        const long long i0 = ((chunk * rows_max) / a.chunks) & ~7ll;
+        const long long i1 = chunk + 1 == a.chunks ? rows_max : (((chunk + 1) * rows_max) / a.chunks) & ~7ll;
+        long long left64 = (i1 < rows ? i1 : rows) - i0;
         if (left64 < 0) left64 = 0;
-        const int left = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const int left = (int)left64;
         const int steps = __reduce_max_sync(mask, left) + LEAD;        // the lanes of a warp walk in step (shuffles)
         const long long p = a.t0 + c2 + i0 * d2;                       // position of the first own output row
         const long long p_lead = p - (long long)LEAD * d2;
@@ -617,7 +627,8 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
         auto ld = [&](int s) -> double {
             if (s >= have) return 0.0;
             const long long pos = p_lead + (long long)s * d2;
-            return (pos >= 0 && pos < a.n_in) ? __ldg(x + pos) : ext_load<true>(x, pos, a.n_in, a.mode);
+            // ldg_early, not __ldg: the compiler sinks plain loads to their first use, and a block without prefetch pays a full HBM latency
+            return (pos >= 0 && pos < a.n_in) ? ldg_early(x + pos) : ext_load<true>(x, pos, a.n_in, a.mode);
         };
         double buf[R];      // the current block's own rows; each is replaced by the next block's row once consumed
 #pragma unroll
@@ -702,20 +713,24 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
         const double *w2 = a.wa + b * a.ldwa;
         const double *w1 = a.wb + b * a.ldwb;
         const long long rows = a.n_out > c2 ? (a.n_out - c2 + d2 - 1) / d2 : 0;
-        const long long i0 = chunk * a.rows_per_chunk;
-        long long left64 = rows - i0;
+        const long long rows_max = (a.n_out + d2 - 1) / d2;           // evenly spread chunk boundaries: see the analysis kernel
+        const long long i0 = ((chunk * rows_max) / a.chunks) & ~7ll;
+        const long long i1 = chunk + 1 == a.chunks ? rows_max : (((chunk + 1) * rows_max) / a.chunks) & ~7ll;
+        long long left64 = (i1 < rows ? i1 : rows) - i0;
         if (left64 < 0) left64 = 0;
-        const int nout = (int)(left64 < a.rows_per_chunk ? left64 : a.rows_per_chunk);
+        const int nout = (int)left64;
         const int steps = __reduce_max_sync(mask, nout + lag);     // consumed own rows: the warp walks in step
         const long long pin0 = a.t0 + c2 + i0 * d2;                // position of consumed own row 0
-        const bool inside = pin0 + (long long)(steps + R) * d2 < a.n_in;   // every row this lane may touch lies inside the row
         const double lam = THR ? a.thr[a.thr_per_row ? b : 0] : 0.0;
         const bool thr_nonneg = !(lam < 0.0);
         auto thr = [&](double v) { return THR ? (thr_nonneg ? vw_threshold_nonneg(v, lam, a.thr_soft) : vw_threshold_value(v, lam, a.thr_soft)) : v; };
+        // rows this lane (or, one step later, its partner) still needs; a short last chunk must not keep loading -- wrapped
+        // or not -- while the longer chunks of its warp finish
+        const int need = nout + lag + 1;
         auto ld2 = [&](const double *rowp, int s) -> double {
-            if (s >= steps) return 0.0;
+            if (s >= need) return 0.0;
             const long long pos = pin0 + (long long)s * d2;
-            return pos < a.n_in ? __ldg(rowp + pos) : ext_load<true>(rowp, pos, a.n_in, a.mode);
+            return pos < a.n_in ? ldg_early(rowp + pos) : ext_load<true>(rowp, pos, a.n_in, a.mode);
         };
         auto ld1 = [&](int s) -> double { return s < LAG1 ? 0.0 : ld2(w1, s - LAG1); };
         const long long step = d2 * (8 * R);
@@ -759,7 +774,9 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
             return out;
         };
         for (int s0 = 0; s0 < steps; s0 += R) {
-            const bool fast = inside && s0 >= lag && s0 + R <= nout + lag && s0 + 2 * R <= steps;
+            // steady state: every row of this block is stored, the whole next block exists and lies inside the row (only the
+            // last blocks of a row's last chunk reach past its end)
+            const bool fast = s0 >= lag && s0 + R <= nout + lag && s0 + 2 * R <= need && pin0 + (long long)(s0 + 2 * R) * d2 <= a.n_in;
             if (__all_sync(mask, fast)) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -816,7 +833,7 @@ bool lattice_for(const vw_ctx *ctx, const VwFilt32 &f, int l, bool qmf, ColLat &
 // waves: with 2-3 resident CTAs per SM a naturally sized grid of ~1800 CTAs ran 4.1 or 6.15 waves, i.e. 12-18 % of the
 // run with most SMs idle (and 2.05 waves -> 68 % at the 2^25-sample spans of an 8-GPU job).
 int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per_sm, dim3 &grid, int &rows_per_chunk,
-             int &chunks_out, int64_t gran = kCR, int64_t want_mul = 6) {
+             int &chunks_out, int64_t gran = kCR, int64_t want_mul = 6, int64_t min_rpc = 4 * kCR) {
     if (d < 1 || d > (1ll << 30)) return VW_EUNSUPPORTED;
     const int64_t rows = (n_out + d - 1) / d;
     // enough (chunk, column) threads to fill the machine several times over, but chunks long enough to amortise the
@@ -825,7 +842,13 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
     int64_t chunks = (want_threads + d * batch - 1) / (d * batch);
     if (chunks < 1) chunks = 1;
     int64_t rpc = (rows + chunks - 1) / chunks;
-    if (rpc < 4 * kCR) rpc = 4 * kCR;
+    {
+        // chunks long enough to amortise the warm-up rows each of them re-reads -- but never fewer lanes than one full wave
+        const int64_t one_wave = (n_out * batch) / ((int64_t)std::max(per_sm, 1) * ctx->sm_count * kCThreads);
+        if (ctx->opt_colrpc > 0 && min_rpc != 4 * kCR) min_rpc = ctx->opt_colrpc;   // developer knob (lattice kernels only)
+        const int64_t floor_rpc = std::max<int64_t>(4 * kCR, std::min(min_rpc, one_wave));
+        if (rpc < floor_rpc) rpc = floor_rpc;
+    }
     rpc = ((rpc + gran - 1) / gran) * gran;
     chunks = (rows + rpc - 1) / rpc;
     int64_t blocks = (chunks * d + kCThreads - 1) / kCThreads;
@@ -874,7 +897,7 @@ int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, i
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat2<15>, kCThreads, 0);
     dim3 grid;
     // fewer, longer chunks than the single-level kernels: every chunk re-reads 3 (L-1) warm-up rows
-    if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+    if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
     k_column_analysis_lat2<15><<<grid, kCThreads, 0, ctx->stream>>>(a);
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice pair) launch");
@@ -893,11 +916,11 @@ int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const doub
     dim3 grid;
     if (thr_dev) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, true>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
         k_column_synthesis_lat2<15, true><<<grid, kCThreads, 0, ctx->stream>>>(a);
     } else {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, false>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3)) return rc;
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
         k_column_synthesis_lat2<15, false><<<grid, kCThreads, 0, ctx->stream>>>(a);
     }
     ctx->launches++;
@@ -929,7 +952,7 @@ int vw_column_analysis(vw_ctx *ctx, const double *x, int64_t ldx, double *v, int
     ColLat lat;
     if (lattice_for(ctx, a.f, l, qmf, lat)) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat<15>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR)) return rc;
+        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR, 6, 480)) return rc;
         k_column_analysis_lat<15><<<grid, kCThreads, 0, ctx->stream>>>(a, lat);
         ctx->launches++;
         return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice) launch");
@@ -968,7 +991,7 @@ int vw_column_synthesis(vw_ctx *ctx, const double *v, int64_t ldv, const double 
     ColLat lat;
     if (lattice_for(ctx, a.f, l, qmf, lat)) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat<15>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR)) return rc;
+        if (int rc = geometry(ctx, n_out, d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kLR, 6, 480)) return rc;
         k_column_synthesis_lat<15><<<grid, kCThreads, 0, ctx->stream>>>(a, lat);
         ctx->launches++;
         return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (lattice) launch");

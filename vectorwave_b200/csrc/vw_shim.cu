@@ -582,6 +582,7 @@ int vw_set_option(vw_ctx *ctx, const char *name, int64_t value) {
     else if (!strcmp(name, "poly")) ctx->opt_poly = value;
     else if (!strcmp(name, "colmin")) ctx->opt_colmin = value;
     else if (!strcmp(name, "lattice")) ctx->opt_lattice = value;
+    else if (!strcmp(name, "colrpc")) ctx->opt_colrpc = value;
     else if (!strcmp(name, "wave")) ctx->opt_wave = value;
     else if (!strcmp(name, "l2pf")) ctx->opt_l2pf = value;
     else if (!strcmp(name, "lean")) ctx->opt_lean = value;
