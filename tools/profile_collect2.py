@@ -69,6 +69,14 @@ if os.path.exists(rep):
                 "`sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active`; issue = `sm__issue_active.avg.pct_of_peak_sustained_elapsed`; "
                 "stalls = `smsp__average_warps_issue_stalled_*_per_issue_active.ratio`.\n")
 
+rep = os.path.join(G, f"prof_{R}_coif5.ncu-rep")
+if os.path.exists(rep):
+    md = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    with open(os.path.join(P, f"{R}_coif5_ncu_full.md"), "w") as f:
+        f.write(f"# `ncu --set full --clock-control none` -- one 2^26-sample signal, coif5, J = 10, PERIODIC (config #4's kernels at 1/4 length) ({R})\n\n"
+                "Levels 1-2: direct-form tile kernels; levels 3-10: lattice column kernels, two levels per launch "
+                f"(`csrc/vw_column.cu`, `csrc/vw_lattice.cu`).\n\n{md}\n")
+
 # ---- per-config traffic ------------------------------------------------------------------------------------------
 traffic_path = os.path.join(P, "traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}

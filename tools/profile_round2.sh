@@ -16,6 +16,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_lean_(analysis|synthesis)" --launch-skip 6 -c 2 \
     -o $O/prof_${R}_bench -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > $O/ncu_full_$R.log 2>&1
 ncu -i $O/prof_${R}_bench.ncu-rep --page source --csv > $O/prof_${R}_bench_source.csv 2>/dev/null
+# config #4's kernels at a quarter of its length: the two coif5 tile levels and the lattice column pairs (one launch of each kind per direction)
+python tools/prof_once.py --warm 0 --log2n 26 > /dev/null 2>&1 &&
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"^k_|::k_" -c 12 -o $O/prof_${R}_coif5 -f \
+    python tools/prof_once.py --warm 0 --log2n 26 > $O/ncu_full_coif5_$R.log 2>&1
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
 cap() {  # name, prof_once args...
   name=$1; shift
