@@ -127,7 +127,7 @@ def eng():
     import vectorwave_b200 as vw
     e = vw.Engine.get()
     yield e
-    for k, v in (("lattice", 1), ("colmin", 0), ("tile", 0), ("fuse", 0)):
+    for k, v in (("lattice", 7), ("colmin", 0), ("tile", 0), ("fuse", 0)):
         e.set_option(k, v)
 
 
@@ -138,7 +138,7 @@ def _both(eng, fn, lattice=3):
     a = fn()
     eng.set_option("lattice", 0)
     b = fn()
-    eng.set_option("lattice", 3)
+    eng.set_option("lattice", 7)
     return a, b
 
 
@@ -202,7 +202,7 @@ def test_pairs_save_launches_and_singles_take_over_where_pairs_do_not_apply(eng)
         l0 = eng.launch_count()
         eng.forward(x, h * S, g * S, 8, mode)
         counts[key] = eng.launch_count() - l0
-    eng.set_option("lattice", 3)
+    eng.set_option("lattice", 7)
     assert counts["singles"] - counts["pairs"] == 3 and counts["symmetric"] == counts["singles"]
 
 
@@ -244,3 +244,56 @@ def test_coif5_span_calls_in_lattice_form_equal_the_unsharded_transform(eng):
     t = REL * float(np.max(np.abs(x)))
     assert float(np.max(np.abs(ws.cpu().numpy().reshape(-1) - np.asarray(wf)[level - 1].reshape(-1)[lo:]))) <= t
     assert float(np.max(np.abs(vs.cpu().numpy().reshape(-1) - np.asarray(vf).reshape(-1)[lo:]))) <= t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("name,b,n,levels", [("sym8", 1, 65536, 8), ("db8", 2, 40001, 7), ("coif3", 3, 9000, 6), ("db10", 2, 30002, 7),
+                                             ("sym8", 2, 4096, 5)])
+def test_direct_form_synthesis_pairs_of_16_to_20_tap_filters_against_the_oracle(eng, mode, name, b, n, levels):
+    """16-20-tap quadrature-mirror pairs fit no lattice (decimal tables), so their deep synthesis levels run two per pass in
+    direct form (DirSynCore in csrc/vw_column.cu): against the oracle, and against the one-level-per-pass kernels (bit 2 of
+    the option off).  SYMMETRIC never pairs (per-level re-mirroring), so there both settings must agree bit for bit."""
+    import vectorwave_b200 as vw
+    from vectorwave_b200.modwt import multilevel_alignment
+    h, g, wid = filters(name)
+    hs, gs = h * S, g * S
+    x = np.random.default_rng(n + mode + levels).standard_normal((b, n))
+    bm = [vw.BoundaryMode.PERIODIC, vw.BoundaryMode.ZERO_PADDING, vw.BoundaryMode.SYMMETRIC][mode]
+    align, order = multilevel_alignment(vw.get_wavelet(name), bm, levels)
+    w = np.empty((levels, b, n))
+    v = np.empty((b, n))
+    refs = []
+    for i in range(b):
+        wo, vo = cref.decompose(x[i], h, g, levels, mode)
+        w[:, i, :], v[i] = wo, vo
+        refs.append(cref.reconstruct(wo, vo, h, g, mode, wid))
+    out = {}
+    for lat in (7, 3):
+        eng.set_option("lattice", lat)
+        eng.inverse(w, v, hs, gs, mode, align, order)           # plan cached
+        l0 = eng.launch_count()
+        out[lat] = (np.asarray(eng.inverse(w, v, hs, gs, mode, align, order)), eng.launch_count() - l0)
+    eng.set_option("lattice", 7)
+    for i in range(b):
+        tr = REL * max(float(np.max(np.abs(refs[i]))), float(np.max(np.abs(x))))
+        assert float(np.max(np.abs(out[7][0][i] - refs[i]))) <= tr
+        assert float(np.max(np.abs(out[3][0][i] - refs[i]))) <= tr
+    if mode == 2:
+        assert np.array_equal(out[7][0], out[3][0])
+    elif (name, n, levels) == ("sym8", 65536, 8):
+        assert out[7][1] < out[3][1]             # config #3's plan: a pair replaces two single-level column launches
+
+
+@pytest.mark.gpu
+def test_direct_form_pairs_threshold_on_load_equals_the_oracle_denoise(eng):
+    h, g, wid = filters("db8")
+    n, levels = 1 << 16, 7
+    x = np.random.default_rng(13).standard_normal((2, n))
+    for mode in (0, 1):
+        den, thr = eng.denoise(x, h * S, g * S, levels, mode, threshold=-1.0, soft=True)
+        den = np.asarray(den)
+        for i in range(2):
+            dref, tref = cref.swt_denoise(x[i], h, g, levels, mode, wid, -1.0, True)
+            assert abs(float(np.asarray(thr)[i]) - tref) <= 1e-12 * tref
+            assert float(np.max(np.abs(den[i] - dref))) <= REL * float(np.max(np.abs(x)))

@@ -553,7 +553,8 @@ __global__ void __launch_bounds__(kCThreads, 3) k_column_synthesis_lat(const __g
 // levels instead of 48), the synthesis reads V_{j+1}, W_{j+1}, W_j and writes V_{j-1}.  State per lane: 3 (K-1) + 2 doubles.
 // Valid where V_j outside the row is what the cascade computes from the extended input: PERIODIC, ZERO_PADDING, span calls --
 // not SYMMETRIC (V_j is re-mirrored per level, ScalarOps.java:818-835), which keeps one level per pass.
-struct ColPair {
+template <class P>
+struct ColPairT {
     const double *x; long long ldx;       // analysis: V_{j-1};  synthesis: V_{j+1}
     const double *wa; long long ldwa;     // synthesis: W_{j+1}
     const double *wb; long long ldwb;     // synthesis: W_j
@@ -563,8 +564,9 @@ struct ColPair {
     long long n_in, t0, n_out, batch, d;  // d = dilation of level j; a lane walks positions c2 + i * 2d, c2 in [0, 2d)
     int rows_per_chunk, chunks, mode;     // rows = a lane's own rows (level-(j+1) rows)
     const double *thr; int thr_per_row, thr_soft;
-    ColLat c;
+    P c;                                  // the arithmetic core's coefficients (lattice, or the low-pass taps of a quadrature-mirror pair)
 };
+typedef ColPairT<ColLat> ColPair;
 
 #ifndef VW_PAIR_CTAS
 #define VW_PAIR_CTAS 2
@@ -689,13 +691,112 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
 }
 
 // Synthesis pair.  A lane consumes (V_{j+1}, W_{j+1}) at own row s, which completes V_j at own row s - (L-1); that value and
-// W_j of the same row go through the level-j cascade, whose two output channels belong to neighbouring level-j rows:
-// V_{j-1}[q] = y0(q + L-2) + y1(q + L-1) -- one term from each lane of the pair (ScalarOps / MultiLevelMODWTTransform.java:554-601
-// index rule t + k d).  The even lane's output lags its consumed row by L-1 + K-1 own rows, the odd lane's by one more.
-template <int K, bool THR>
-__global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_lat2(const __grid_constant__ ColPair a) {
-    constexpr int L = 2 * K, R = kPR;
-    constexpr int LAG1 = L - 1;            // own rows between a consumed (V, W)_{j+1} row and the V_j row it completes
+// W_j of the same row go into level j, whose outputs mix the parities (index rule t + k d, MultiLevelMODWTTransform.java:554-601):
+// one value per row crosses the lane pair by shuffle.  The skeleton (lanes, chunks, prefetch, stores) is shared by two
+// arithmetic cores: the lattice (long filters whose table fits one) and the direct transposed form (16-20-tap quadrature-mirror
+// pairs, whose decimal tables fit no lattice).  The even lane's output lags its consumed row by LAG1 + LAG0 own rows, the odd
+// lane's by one more.
+template <int K> struct LatSynCore {
+    typedef ColLat Params;
+    static constexpr int LAG1 = 2 * K - 1;     // own rows between a consumed (V, W)_{j+1} row and the V_j row it completes
+    static constexpr int LAG0 = K - 1;         // ... between that V_j row and the even lane's V_{j-1} row it completes
+    static constexpr int CTAS = VW_PAIR_CTAS;
+    double dl1[K - 1], dl2[K - 1][2], y0prev, z0prev;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
+        y0prev = z0prev = 0.0;
+    }
+    // V_{j-1}[q] = y0(q + L-2) + y1(q + L-1): one term from each lane of the pair
+    __device__ __forceinline__ double row(const Params &c, int r, int rho, unsigned mask, double cv, double cw2, double cw1) {
+        double aa = cv, bb = cw2;
+#pragma unroll
+        for (int k = K - 2; k >= 0; k--) {
+            const double an = fma(-c.t[k], bb, aa);
+            bb = fma(c.t[k], aa, bb);
+            aa = dl2[k][r & 1];
+            dl2[k][r & 1] = an;
+        }
+        const double y0 = fma(c.b[2], bb, c.b[0] * aa);
+        const double y1 = fma(c.b[3], bb, c.b[1] * aa);
+        aa = y0prev + y1;               // V_j at own row s - (L-1)
+        y0prev = y0;
+        bb = cw1;
+#pragma unroll
+        for (int k = K - 2; k >= 0; k--) {
+            const double an = fma(-c.t[k], bb, aa);
+            bb = fma(c.t[k], aa, bb);
+            aa = dl1[k];
+            dl1[k] = an;
+        }
+        const double z0 = fma(c.b[2], bb, c.b[0] * aa);
+        const double z1 = fma(c.b[3], bb, c.b[1] * aa);
+        const double z1n = shfl_partner(mask, z1);
+        const double out = (rho ? z0prev : z0) + z1n;
+        z0prev = z0;
+        return out;
+    }
+    __device__ __forceinline__ void end_block() {}
+};
+
+// Direct (transposed) form.  acc2[j]: V_j at own row (block start - (L-1) + j), fed by every consumed row with all L taps;
+// acc1[j]: V_{j-1} at the own output row that completes at in-block step j, fed per step by 8 even taps of the lane's own V_j
+// row and 8 odd taps of the partner's.  The odd lane applies its own row one step late, which makes the accumulator indices
+// the same compile-time constants on both lanes (its outputs then complete one step later than the even lane's: lag + 1).
+struct DirTaps { double h[VW_LEAN_MAX_L]; };
+template <int L> struct DirSynCore {
+    typedef DirTaps Params;
+    static constexpr int R = VW_PAIR_R, H = L / 2;
+    static constexpr int LAG1 = L - 1, LAG0 = H - 1;
+#ifndef VW_DIR_CTAS
+#define VW_DIR_CTAS 3
+#endif
+    static constexpr int CTAS = VW_DIR_CTAS;
+    double acc2[L - 1 + R], acc1[H - 1 + R], v1prev, w1prev;
+    static __device__ __forceinline__ double gk(const Params &c, int k) { return (k & 1) ? -c.h[L - 1 - k] : c.h[L - 1 - k]; }
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < L - 1 + R; j++) acc2[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < H - 1 + R; j++) acc1[j] = 0.0;
+        v1prev = w1prev = 0.0;
+    }
+    __device__ __forceinline__ double row(const Params &c, int r, int rho, unsigned mask, double cv, double cw2, double cw1) {
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            const int j = L - 1 + r - k;
+            acc2[j] = fma(c.h[k], cv, acc2[j]);
+            acc2[j] = fma(gk(c, k), cw2, acc2[j]);
+        }
+        const double v1 = acc2[r];                          // V_j at own row s - (L-1): complete
+        const double pv = shfl_partner(mask, v1), pw = shfl_partner(mask, cw1);
+        const double ov = rho ? v1prev : v1, ow = rho ? w1prev : cw1;
+        v1prev = v1; w1prev = cw1;
+#pragma unroll
+        for (int kk = 0; kk < H; kk++) {
+            const int j = H - 1 + r - kk;
+            acc1[j] = fma(c.h[2 * kk], ov, acc1[j]);
+            acc1[j] = fma(gk(c, 2 * kk), ow, acc1[j]);
+            acc1[j] = fma(c.h[2 * kk + 1], pv, acc1[j]);
+            acc1[j] = fma(gk(c, 2 * kk + 1), pw, acc1[j]);
+        }
+        return acc1[r];
+    }
+    __device__ __forceinline__ void end_block() {
+#pragma unroll
+        for (int j = 0; j < L - 1; j++) acc2[j] = acc2[j + R];
+#pragma unroll
+        for (int j = L - 1; j < L - 1 + R; j++) acc2[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < H - 1; j++) acc1[j] = acc1[j + R];
+#pragma unroll
+        for (int j = H - 1; j < H - 1 + R; j++) acc1[j] = 0.0;
+    }
+};
+
+template <class Core, bool THR>
+__global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_synthesis_pair(const __grid_constant__ ColPairT<typename Core::Params> a) {
+    constexpr int R = kPR, LAG1 = Core::LAG1;
     static_assert(R % 2 == 0, "delay slots must be compile-time registers");
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
     const long long d2 = 2 * a.d;
@@ -706,8 +807,7 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
     const long long c2 = (pid - chunk * a.d) + (rho ? a.d : 0);
     const unsigned mask = __ballot_sync(0xffffffffu, chunk < a.chunks);
     if (chunk >= a.chunks) return;
-    const ColLat &c = a.c;
-    const int lag = LAG1 + (K - 1) + rho;     // own rows between a consumed row and the output row it completes
+    const int lag = LAG1 + Core::LAG0 + rho;     // own rows between a consumed row and the output row it completes
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const double *v2 = a.x + b * a.ldx;
         const double *w2 = a.wa + b * a.ldwa;
@@ -738,41 +838,11 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
         const char *w2p = reinterpret_cast<const char *>(w2 + pin0);
         const char *w1p = reinterpret_cast<const char *>(w1 + pin0) - d2 * (8 * LAG1);
         char *op = reinterpret_cast<char *>(a.o0 + b * a.ldo0 + c2 + i0 * d2) - d2 * (8 * (long long)lag);
-        double dl1[K - 1], dl2[K - 1][2];
-#pragma unroll
-        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
-        double y0prev = 0.0, z0prev = 0.0;
+        Core core;
+        core.init();
         double bv[R], bw2[R], bw1[R];
 #pragma unroll
         for (int r = 0; r < R; r++) { bv[r] = ld2(v2, r); bw2[r] = ld2(w2, r); bw1[r] = ld1(r); }
-        auto row = [&](int r, double cv, double cw2, double cw1) -> double {
-            double aa = cv, bb = cw2;
-#pragma unroll
-            for (int k = K - 2; k >= 0; k--) {
-                const double an = fma(-c.t[k], bb, aa);
-                bb = fma(c.t[k], aa, bb);
-                aa = dl2[k][r & 1];
-                dl2[k][r & 1] = an;
-            }
-            const double y0 = fma(c.b[2], bb, c.b[0] * aa);
-            const double y1 = fma(c.b[3], bb, c.b[1] * aa);
-            aa = y0prev + y1;               // V_j at own row s - (L-1)
-            y0prev = y0;
-            bb = cw1;
-#pragma unroll
-            for (int k = K - 2; k >= 0; k--) {
-                const double an = fma(-c.t[k], bb, aa);
-                bb = fma(c.t[k], aa, bb);
-                aa = dl1[k];
-                dl1[k] = an;
-            }
-            const double z0 = fma(c.b[2], bb, c.b[0] * aa);
-            const double z1 = fma(c.b[3], bb, c.b[1] * aa);
-            const double z1n = shfl_partner(mask, z1);
-            const double out = (rho ? z0prev : z0) + z1n;
-            z0prev = z0;
-            return out;
-        };
         for (int s0 = 0; s0 < steps; s0 += R) {
             // steady state: every row of this block is stored, the whole next block exists and lies inside the row (only the
             // last blocks of a row's last chunk reach past its end)
@@ -784,7 +854,7 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
                     bv[r] = ldg_early(row_ptr(v2p, d2i, R + r));
                     bw2[r] = ldg_early(row_ptr(w2p, d2i, R + r));
                     bw1[r] = ldg_early(row_ptr(w1p, d2i, R + r));
-                    *row_ptr(op, d2i, r) = row(r, cv, cw2, cw1);
+                    *row_ptr(op, d2i, r) = core.row(a.c, r, rho, mask, cv, cw2, cw1);
                 }
             } else {
 #pragma unroll
@@ -793,10 +863,11 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_synthesis_la
                     bv[r] = ld2(v2, s0 + R + r);
                     bw2[r] = ld2(w2, s0 + R + r);
                     bw1[r] = ld1(s0 + R + r);
-                    const double o = row(r, cv, cw2, cw1);
+                    const double o = core.row(a.c, r, rho, mask, cv, cw2, cw1);
                     if (s0 + r >= lag && s0 + r < nout + lag) *row_ptr(op, d2i, r) = o;
                 }
             }
+            core.end_block();
             v2p += step; w2p += step; w1p += step; op += step;
         }
     }
@@ -874,6 +945,7 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
 
 }  // namespace
 
+static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid);
 // Levels j and j+1 (d = dilation of level j) in one pass; VW_EUNSUPPORTED when the pair form does not apply (the caller
 // then runs the two levels one by one).
 static bool pair_ok(const vw_ctx *ctx, const VwFilt &f, int l, int64_t d, int mode, ColLat &c) {
@@ -898,33 +970,75 @@ int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, i
     dim3 grid;
     // fewer, longer chunks than the single-level kernels: every chunk re-reads 3 (L-1) warm-up rows
     if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
+    fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
     k_column_analysis_lat2<15><<<grid, kCThreads, 0, ctx->stream>>>(a);
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice pair) launch");
 }
 
-int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const double *w2, int64_t ldw2, const double *w1,
-                         int64_t ldw1, double *out, int64_t ldo, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch,
-                         const VwFilt &f, int l, int64_t d, int mode, const double *thr_dev, int thr_per_row, int thr_soft) {
-    ColPair a;
-    if (n_out < 1 || batch < 1 || !v2 || !w2 || !w1 || !pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+// The pair kernels spread their chunk boundaries evenly themselves (rows_per_chunk is not used), so the chunk count is free:
+// in a batch (one grid row per signal) make the lanes of a signal fill whole CTAs -- 3 chunks x 32 lanes would leave a
+// quarter of every CTA idle (config #3, levels 5-6: rows of 2048 own rows)
+static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid) {
+    if (batch <= 1 || d2 >= kCThreads || (kCThreads % d2) != 0) return;
+    const int64_t q = kCThreads / d2;                              // chunks per CTA
+    const int64_t rows = (n_out + d2 - 1) / d2;
+    int64_t c = ((chunks + q - 1) / q) * q;
+    while (c > q && rows / c < 256) c -= q;                        // keep chunks long against their warm-up rows
+    if (rows / c < 64) return;
+    chunks = (int)c;
+    grid.x = (unsigned)((c * d2 + kCThreads - 1) / kCThreads);
+}
+
+template <class Core, class A>
+static int launch_pair_synthesis(vw_ctx *ctx, A &a, int64_t n_out, int64_t d, int64_t batch, bool thr) {
+    int per_sm = 0;
+    dim3 grid;
+    if (thr) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, true>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
+        fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
+        k_column_synthesis_pair<Core, true><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, false>, kCThreads, 0);
+        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
+        fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
+        k_column_synthesis_pair<Core, false><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (pair) launch");
+}
+
+template <class A>
+static void fill_pair_synthesis(A &a, const double *v2, int64_t ldv2, const double *w2, int64_t ldw2, const double *w1, int64_t ldw1,
+                                double *out, int64_t ldo, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, int64_t d, int mode,
+                                const double *thr_dev, int thr_per_row, int thr_soft) {
     a.x = v2; a.ldx = ldv2; a.wa = w2; a.ldwa = ldw2; a.wb = w1; a.ldwb = ldw1;
     a.o0 = out; a.ldo0 = ldo; a.o1 = a.o2 = nullptr; a.ldo1 = a.ldo2 = 0;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.mode = mode;
     a.thr = thr_dev; a.thr_per_row = thr_per_row; a.thr_soft = thr_soft;
-    int per_sm = 0;
-    dim3 grid;
-    if (thr_dev) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, true>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
-        k_column_synthesis_lat2<15, true><<<grid, kCThreads, 0, ctx->stream>>>(a);
-    } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_lat2<15, false>, kCThreads, 0);
-        if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
-        k_column_synthesis_lat2<15, false><<<grid, kCThreads, 0, ctx->stream>>>(a);
+}
+
+int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const double *w2, int64_t ldw2, const double *w1,
+                         int64_t ldw1, double *out, int64_t ldo, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch,
+                         const VwFilt &f, int l, int64_t d, int mode, const double *thr_dev, int thr_per_row, int thr_soft) {
+    if (n_out < 1 || batch < 1 || !v2 || !w2 || !w1) return VW_EUNSUPPORTED;
+    if (l == 30) {
+        ColPair a;
+        if (!pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+        fill_pair_synthesis(a, v2, ldv2, w2, ldw2, w1, ldw1, out, ldo, n_in, t0, n_out, batch, d, mode, thr_dev, thr_per_row, thr_soft);
+        return launch_pair_synthesis<LatSynCore<15>>(ctx, a, n_out, d, batch, thr_dev != nullptr);
     }
-    ctx->launches++;
-    return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (lattice pair) launch");
+    // 16-20-tap quadrature-mirror pairs: direct form (their decimal tables fit no lattice)
+    if (!(ctx->opt_lattice & 4) || mode == VW_SYMMETRIC || d < 1 || d > (1ll << 28) || (l != 16 && l != 18 && l != 20) ||
+        !vw_is_qmf(f.h, f.g, l))
+        return VW_EUNSUPPORTED;
+    ColPairT<DirTaps> a;
+    for (int k = 0; k < VW_LEAN_MAX_L; k++) a.c.h[k] = k < l ? f.h[k] : 0.0;
+    fill_pair_synthesis(a, v2, ldv2, w2, ldw2, w1, ldw1, out, ldo, n_in, t0, n_out, batch, d, mode, thr_dev, thr_per_row, thr_soft);
+    if (l == 16) return launch_pair_synthesis<DirSynCore<16>>(ctx, a, n_out, d, batch, thr_dev != nullptr);
+    if (l == 18) return launch_pair_synthesis<DirSynCore<18>>(ctx, a, n_out, d, batch, thr_dev != nullptr);
+    return launch_pair_synthesis<DirSynCore<20>>(ctx, a, n_out, d, batch, thr_dev != nullptr);
 }
 
 int vw_column_min_level(const vw_ctx *ctx, int l, bool forward) {

@@ -822,23 +822,29 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
     out.clear();
     // FP64-bound filters (l >= 24) gain nothing from sharing a launch -- the halo recompute only adds FMAs (measured on coif5)
     // 16-20 taps are FP64-pipe bound in the analysis: two levels per launch keep the halo recompute small (sym8 J = 8 forward
-    // 1.62 -> 1.57 ms, db8 J = 6 4.58 -> 4.39); the synthesis, which re-reads a W halo per level either way, prefers four
-    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : (l >= 16 && forward ? 2 : 4));
+    // 1.62 -> 1.57 ms, db8 J = 6 4.58 -> 4.39); the synthesis of those filters prefers three (db8 J = 6 N = 2^20 inverse: 1-3 | 4-5 |
+    // 6 column 5.1-5.6 ms vs 1-4 | 5-6 5.7-5.8 ms, tools/gpu_r2_plans.sh), shorter filters four
+    const int cap = ctx->opt_fuse > 0 ? (int)std::min<int64_t>(ctx->opt_fuse, 6) : (l >= 24 ? 1 : (l >= 16 ? (forward ? 2 : 3) : 4));
     const double kGeneric = 60.0;  // per-level kernels: one thread per output through L1/L2
     std::vector<double> best(levels + 1, INFINITY);
     std::vector<VwPlanGroup> pick(levels + 1);
     best[0] = 0.0;
     for (int done = 0; done < levels; done++) {
         if (best[done] == INFINITY) continue;
-        // two column levels per pass: the lattice pair kernels (vw_column.cu) exist for 30 taps; a pair the kernels decline at
+        // two column levels per pass: the lattice pair kernels (vw_column.cu) exist for 30 taps (both directions); a pair the kernels decline at
         // run time (a table that fits no lattice, SYMMETRIC) is run level by level by the cascade drivers
-        const bool pair_len = l == 30 && (ctx->opt_lattice & 2) && ctx->opt_poly != 0 && done + 1 >= vw_column_min_level(ctx, l, forward);
+        // ... and, for the synthesis of 16-20-tap quadrature-mirror pairs, in direct form from dilation 8 on
+        const bool pair16 = !forward && (l == 16 || l == 18 || l == 20) && (ctx->opt_lattice & 4) &&
+                            done + 1 >= (ctx->opt_colmin > 0 ? (int)ctx->opt_colmin : 4);
+        const bool pair_len = ctx->opt_poly != 0 &&
+                              ((l == 30 && (ctx->opt_lattice & 2) && done + 1 >= vw_column_min_level(ctx, l, forward)) || pair16);
         for (int nf = 1; nf <= std::max(cap, pair_len ? 2 : 1) && done + nf <= levels; nf++) {
             int64_t tile;
             double c = nf <= cap ? group_cost(ctx, forward, l, done + 1, nf, n, &tile) : INFINITY;
             if (nf > cap) tile = -1;
             if (nf == 2 && pair_len && (int64_t)3 * (l - 1) * (1ll << done) <= n) {
-                const double cpair = std::max(2.0 * (l + 3) / 64.0 / 0.80, 32.0 / 22.5 / 0.80) + 0.1;   // two levels: 32 B/sample
+                const double dfma = l == 30 ? 2.0 * (l + 3) : 4.0 * l;                              // lattice / direct form, two levels
+                const double cpair = std::max(dfma / 64.0 / 0.80, 32.0 / 22.5 / 0.80) + 0.1;        // two levels: 32 B/sample
                 if (cpair < c) { c = cpair; tile = -2; }
             }
             if (nf == 1 && done + 1 >= vw_column_min_level(ctx, l, forward) && ctx->opt_poly != 0) {
