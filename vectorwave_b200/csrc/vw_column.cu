@@ -583,9 +583,12 @@ __device__ __forceinline__ double shfl_partner(unsigned mask, double v) {
     return __shfl_xor_sync(mask, v, 1);
 }
 
+#ifndef VW_PAIR_RA
+#define VW_PAIR_RA 8      // own rows per block of the analysis pair (16 measured: config #4 forward 10.15 -> 10.7 ms, the unrolled body doubles)
+#endif
 template <int K>
 __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat2(const __grid_constant__ ColPair a) {
-    constexpr int L = 2 * K, R = kPR;
+    constexpr int L = 2 * K, R = VW_PAIR_RA;
     // V_{j+1} at own row i needs V_j at own rows i-(L-1) .. i, each of which needs L-1 level-j rows = L/2 own rows more
     constexpr int LEAD = ((L - 1 + L / 2 + R - 1) / R) * R;
     static_assert(R % 2 == 0 && LEAD % 2 == 0, "delay slots must be compile-time registers");
