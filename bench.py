@@ -318,7 +318,9 @@ def roofline_entry(c, key, l, levels, samples, fwd_ms, inv_ms, launches_fwd, lau
             "forward_ms": fwd_ms, "inverse_ms": inv_ms, "forward_frac": alg / fwd_ms * 1e-6 / c.peak,
             "inverse_frac": alg / inv_ms * 1e-6 / c.peak, "launches_forward": launches_fwd, "launches_inverse": launches_inv,
             "fp64_tflops_achieved": 2.0 * 4.0 * l * levels * samples / step_ms * 1e-9, "fp64_tflops_peak_measured": c.fp64_peak,
-            "frac_of_fp64": (2.0 * 4.0 * l * levels * samples / step_ms * 1e-9) / c.fp64_peak if c.fp64_peak else None}
+            "frac_of_fp64": (2.0 * 4.0 * l * levels * samples / step_ms * 1e-9) / c.fp64_peak if c.fp64_peak else None,
+            "fp64_note": "algorithmic FLOPs of the direct form (4L per sample, level and direction, SURVEY 8d)" +
+                         ("; coif5's levels 3-10 run in lattice form and execute L + 2 FP64 instructions per sample and level instead of 2L" if l == 30 else "")}
 
 
 def extra_batch(c, key, workload, mode, rows=None, reps=8):
@@ -440,7 +442,9 @@ def extra_span(c, reps=4):
                         "frac": 48.0 * levels * n_local / ms * 1e-6 / c.peak, "traffic": traffic_of("single2p28_coif5_J10"),
                         "fp64_tflops_achieved": 8.0 * 30 * levels * n_local / ms * 1e-9, "fp64_tflops_peak_measured": c.fp64_peak,
                         "frac_of_fp64": 8.0 * 30 * levels * n_local / ms * 1e-9 / c.fp64_peak if c.fp64_peak else None,
-                        "note": "per GPU, whole step; coif5's 30 taps put the column kernels within 12 % of the FP64 roof too"},
+                        "note": "per GPU, whole step.  fp64_* count the DIRECT form's 4L FLOP per sample, level and direction (the "
+                                "algorithmic work of SURVEY 8d); levels 3-10 run in lattice form (L + 2 FP64 instructions instead of 2L, "
+                                "two levels per pass at 32 B/sample), so the FP64 pipe executes about 60 % of that figure"},
            "roofline_model_gsamples": model * c.world, "frac_of_roofline_model": n_total / ms * 1e-6 / (model * c.world),
            "l2": "per-rank working set 26 GiB / world, far larger than L2"}
     assert rt < 1e-9, f"span round trip error {rt}"
