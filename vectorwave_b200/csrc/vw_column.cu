@@ -11,6 +11,9 @@
 // Analysis:   V_j[p] = sum_k hs[k] X[ext(p - k d)],  W_j[p] likewise with gs       (ScalarOps.java:700-723,790-835)
 // Synthesis:  out[p] = sum_k hs[k] V[ext(p + sh (k d - th))] + sum_k gs[k] W[ext(p + sg (k d - tg))]
 //             (MultiLevelMODWTTransform.java:554-645; sigma = -1 streams are run with reversed taps)
+#include <mutex>
+#include <vector>
+
 #include "vw_internal.cuh"
 
 namespace {
@@ -569,18 +572,43 @@ struct ColPairT {
 typedef ColPairT<ColLat> ColPair;
 
 #ifndef VW_PAIR_CTAS
-#define VW_PAIR_CTAS 2
+#define VW_PAIR_CTAS 3
 #endif
 #ifndef VW_PAIR_R
 #define VW_PAIR_R 8
 #endif
-// Measured on config #4 (tools/gpu_r2_pairab.sh): 2 CTAs/SM at ~250 registers beat 3 CTAs/SM with spills (forward 10.1 vs
-// 10.7 ms, inverse 10.4 vs 13.5), 8 rows per block beat 4, and a prefetch.global.L2 32 / 64 rows ahead of the register
-// prefetch changed nothing that survives a repeat (forward -2 %, inverse +5 %) -- not kept.
+// Measured on config #4 (tools/gpu_r2_pairab.sh, gpu_r2_ring.sh).  With the input rows prefetched into registers (one block of
+// 8 rows ahead) the kernels needed ~250 registers: 2 CTAs/SM beat 3 CTAs/SM with spills (forward 10.1 vs 10.7 ms, inverse 10.4
+// vs 13.5), 8 rows per block beat 4 and 16, a prefetch.global.L2 32 / 64 rows ahead changed nothing repeatable.  With the rows
+// in a shared-memory ring filled by cp.async (below) the same kernels fit 168 registers without spills worth the name: 3 CTAs/SM
+// with a ring of 2 blocks beat 2 CTAs/SM with a ring of 4 (config #4 14.0 vs 13.5-14.0 GSamples/s, its 2^25-sample spans 11.9 vs
+// 11.5, sym8 J = 8 inverse 1.81 vs 2.10 ms).
 constexpr int kPR = VW_PAIR_R;    // own rows per block (even: the level-(j+1) delay slots are compile-time registers)
 
 __device__ __forceinline__ double shfl_partner(unsigned mask, double v) {
     return __shfl_xor_sync(mask, v, 1);
+}
+
+// Input rows of the pair kernels travel through a per-lane ring in shared memory, filled by 8-byte cp.async: ncu showed the
+// pairs read-latency bound (long_scoreboard 1.3-3.2 warps per issue at 8 warps/SM) with a register prefetch of one block (8
+// rows) -- all the ~250 registers allowed.  The ring holds kPD blocks per stream and costs no registers (which is what lets a
+// third CTA onto the SM): rows are requested (kPD-1) blocks before they are used.  Slot [row mod (kPD*R)][thread]: a lane only ever touches its own column of the ring,
+// so neither barriers nor bank conflicts; rows outside the signal (wrap, zero padding) are written with plain stores.
+#ifndef VW_PAIR_DEPTH
+#define VW_PAIR_DEPTH 2
+#endif
+constexpr int kPD = VW_PAIR_DEPTH;
+extern __shared__ __align__(16) double pair_ring[];
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t dst, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst), "d"(v) : "memory"); }
+__device__ __forceinline__ double lds64(uint32_t src) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(src) : "memory");
+    return v;
 }
 
 #ifndef VW_PAIR_RA
@@ -628,16 +656,23 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
         for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
         double xprev = 0.0, vprev = 0.0;
         const int have = LEAD + left;          // own rows that exist from step 0 on (warm-up + outputs)
-        // generic load of own row s (counted from the first warm-up row)
-        auto ld = [&](int s) -> double {
-            if (s >= have) return 0.0;
+        constexpr int RING = kPD * R;          // rows in the ring (a power of two)
+        static_assert((RING & (RING - 1)) == 0, "ring slots are taken modulo a power of two");
+        const uint32_t ring = (uint32_t)__cvta_generic_to_shared(pair_ring) + threadIdx.x * 8u;
+        auto slot = [&](int s) { return ring + (uint32_t)(s & (RING - 1)) * (kCThreads * 8u); };
+        // request own row s (counted from the first warm-up row) into its ring slot
+        auto fetch = [&](int s) {
+            if (s >= have) { sts64(slot(s), 0.0); return; }
             const long long pos = p_lead + (long long)s * d2;
-            // ldg_early, not __ldg: the compiler sinks plain loads to their first use, and a block without prefetch pays a full HBM latency
-            return (pos >= 0 && pos < a.n_in) ? ldg_early(x + pos) : ext_load<true>(x, pos, a.n_in, a.mode);
+            if (pos >= 0 && pos < a.n_in) cp_async8(slot(s), x + pos);
+            else sts64(slot(s), ext_load<true>(x, pos, a.n_in, a.mode));
         };
-        double buf[R];      // the current block's own rows; each is replaced by the next block's row once consumed
+        // one commit group per block, so that "all but the newest kPD-1 groups" means "the current block" from the first iteration on
 #pragma unroll
-        for (int r = 0; r < R; r++) buf[r] = ld(r);
+        for (int r = 0; r < (kPD - 1) * R; r++) {
+            fetch(r);
+            if ((r + 1) % R == 0) cp_async_commit();
+        }
         auto row = [&](int r, double xv, double &w1, double &v2, double &w2) {
             // the neighbouring level-j row: the even lane needs the odd lane's PREVIOUS row, the odd lane the even lane's current one
             const double un = shfl_partner(mask, rho ? xprev : xv);
@@ -667,22 +702,30 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
             v2 = a2; w2 = b2;
         };
         for (int s0 = 0; s0 < steps; s0 += R) {
-            // steady state for the whole warp: every lane stores this whole block and prefetches a whole block inside the row
-            const bool fast = s0 >= LEAD && s0 + 2 * R <= have;
+            // steady state for the whole warp: every lane stores this whole block, and the block requested now -- (kPD-1) blocks
+            // ahead -- lies inside the row
+            const bool fast = s0 >= LEAD && s0 + kPD * R <= have;
+            const uint32_t cur = slot(s0), ahead = slot(s0 + (kPD - 1) * R);     // blocks never straddle the ring's end
             if (__all_sync(mask, fast)) {
 #pragma unroll
+                for (int r = 0; r < R; r++) cp_async8(ahead + r * (kCThreads * 8u), row_ptr(xp, d2i, (kPD - 1) * R + r));
+                cp_async_commit();
+                cp_async_wait<kPD - 1>();
+#pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const double xv = buf[r];
-                    buf[r] = ldg_early(row_ptr(xp, d2i, R + r));
+                    const double xv = lds64(cur + r * (kCThreads * 8u));
                     double w1, v2, w2;
                     row(r, xv, w1, v2, w2);
                     *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2;
                 }
             } else {
 #pragma unroll
+                for (int r = 0; r < R; r++) fetch(s0 + (kPD - 1) * R + r);
+                cp_async_commit();
+                cp_async_wait<kPD - 1>();
+#pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const double xv = buf[r];
-                    buf[r] = ld(s0 + R + r);
+                    const double xv = lds64(cur + r * (kCThreads * 8u));
                     double w1, v2, w2;
                     row(r, xv, w1, v2, w2);
                     if (s0 + r >= LEAD && s0 + r < have) { *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2; }
@@ -690,6 +733,7 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
             }
             xp += step; vp += step; w1p += step; w2p += step;
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -703,7 +747,10 @@ template <int K> struct LatSynCore {
     typedef ColLat Params;
     static constexpr int LAG1 = 2 * K - 1;     // own rows between a consumed (V, W)_{j+1} row and the V_j row it completes
     static constexpr int LAG0 = K - 1;         // ... between that V_j row and the even lane's V_{j-1} row it completes
-    static constexpr int CTAS = VW_PAIR_CTAS;
+#ifndef VW_PAIR_DEPTH_SYN
+#define VW_PAIR_DEPTH_SYN VW_PAIR_DEPTH
+#endif
+    static constexpr int CTAS = VW_PAIR_CTAS, DEPTH = VW_PAIR_DEPTH_SYN;
     double dl1[K - 1], dl2[K - 1][2], y0prev, z0prev;
     __device__ __forceinline__ void init() {
 #pragma unroll
@@ -754,7 +801,10 @@ template <int L> struct DirSynCore {
 #ifndef VW_DIR_CTAS
 #define VW_DIR_CTAS 3
 #endif
-    static constexpr int CTAS = VW_DIR_CTAS;
+#ifndef VW_DIR_DEPTH
+#define VW_DIR_DEPTH 2
+#endif
+    static constexpr int CTAS = VW_DIR_CTAS, DEPTH = VW_DIR_DEPTH;
     double acc2[L - 1 + R], acc1[H - 1 + R], v1prev, w1prev;
     static __device__ __forceinline__ double gk(const Params &c, int k) { return (k & 1) ? -c.h[L - 1 - k] : c.h[L - 1 - k]; }
     __device__ __forceinline__ void init() {
@@ -799,7 +849,7 @@ template <int L> struct DirSynCore {
 
 template <class Core, bool THR>
 __global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_synthesis_pair(const __grid_constant__ ColPairT<typename Core::Params> a) {
-    constexpr int R = kPR, LAG1 = Core::LAG1;
+    constexpr int R = kPR, LAG1 = Core::LAG1, PD = Core::DEPTH;
     static_assert(R % 2 == 0, "delay slots must be compile-time registers");
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
     const long long d2 = 2 * a.d;
@@ -830,12 +880,24 @@ __global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_synthesis_pair
         // rows this lane (or, one step later, its partner) still needs; a short last chunk must not keep loading -- wrapped
         // or not -- while the longer chunks of its warp finish
         const int need = nout + lag + 1;
-        auto ld2 = [&](const double *rowp, int s) -> double {
-            if (s >= need) return 0.0;
+        constexpr int RING = PD * R;
+        static_assert((RING & (RING - 1)) == 0, "ring slots are taken modulo a power of two");
+        const uint32_t ring = (uint32_t)__cvta_generic_to_shared(pair_ring) + threadIdx.x * 8u;
+        constexpr uint32_t kRow = kCThreads * 8u, kStream = RING * kCThreads * 8u;     // bytes per ring row / per stream
+        auto slot = [&](int s) { return ring + (uint32_t)(s & (RING - 1)) * kRow; };
+        // request consumed row s of V_{j+1}, W_{j+1} and row s - LAG1 of W_j into their ring slots
+        auto fetch2 = [&](const double *rowp, uint32_t dst, int s) {
+            if (s < 0 || s >= need) { sts64(dst, 0.0); return; }
             const long long pos = pin0 + (long long)s * d2;
-            return pos < a.n_in ? ldg_early(rowp + pos) : ext_load<true>(rowp, pos, a.n_in, a.mode);
+            if (pos < a.n_in) cp_async8(dst, rowp + pos);
+            else sts64(dst, ext_load<true>(rowp, pos, a.n_in, a.mode));
         };
-        auto ld1 = [&](int s) -> double { return s < LAG1 ? 0.0 : ld2(w1, s - LAG1); };
+        auto fetch = [&](int s) {
+            const uint32_t dst = slot(s);
+            fetch2(v2, dst, s);
+            fetch2(w2, dst + kStream, s);
+            fetch2(w1, dst + 2 * kStream, s - LAG1);
+        };
         const long long step = d2 * (8 * R);
         const char *v2p = reinterpret_cast<const char *>(v2 + pin0);                 // consumed own row 0 of the CURRENT block
         const char *w2p = reinterpret_cast<const char *>(w2 + pin0);
@@ -843,29 +905,40 @@ __global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_synthesis_pair
         char *op = reinterpret_cast<char *>(a.o0 + b * a.ldo0 + c2 + i0 * d2) - d2 * (8 * (long long)lag);
         Core core;
         core.init();
-        double bv[R], bw2[R], bw1[R];
+        // one commit group per block, so that "all but the newest PD-1 groups" means "the current block" from the first iteration on
 #pragma unroll
-        for (int r = 0; r < R; r++) { bv[r] = ld2(v2, r); bw2[r] = ld2(w2, r); bw1[r] = ld1(r); }
+        for (int r = 0; r < (PD - 1) * R; r++) {
+            fetch(r);
+            if ((r + 1) % R == 0) cp_async_commit();
+        }
         for (int s0 = 0; s0 < steps; s0 += R) {
-            // steady state: every row of this block is stored, the whole next block exists and lies inside the row (only the
-            // last blocks of a row's last chunk reach past its end)
-            const bool fast = s0 >= lag && s0 + R <= nout + lag && s0 + 2 * R <= need && pin0 + (long long)(s0 + 2 * R) * d2 <= a.n_in;
+            // steady state: every row of this block is stored; the block requested now -- (PD-1) blocks ahead -- exists in all
+            // three streams and lies inside the row (only the last blocks of a row's last chunk reach past its end)
+            const bool fast = s0 >= lag && s0 + R <= nout + lag && s0 + PD * R <= need && s0 + (PD - 1) * R >= LAG1 &&
+                              pin0 + (long long)(s0 + PD * R) * d2 <= a.n_in;
+            const uint32_t cur = slot(s0), ahead = slot(s0 + (PD - 1) * R);     // blocks never straddle the ring's end
             if (__all_sync(mask, fast)) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const double cv = bv[r], cw2 = thr(bw2[r]), cw1 = thr(bw1[r]);
-                    bv[r] = ldg_early(row_ptr(v2p, d2i, R + r));
-                    bw2[r] = ldg_early(row_ptr(w2p, d2i, R + r));
-                    bw1[r] = ldg_early(row_ptr(w1p, d2i, R + r));
+                    cp_async8(ahead + r * kRow, row_ptr(v2p, d2i, (PD - 1) * R + r));
+                    cp_async8(ahead + r * kRow + kStream, row_ptr(w2p, d2i, (PD - 1) * R + r));
+                    cp_async8(ahead + r * kRow + 2 * kStream, row_ptr(w1p, d2i, (PD - 1) * R + r));
+                }
+                cp_async_commit();
+                cp_async_wait<PD - 1>();
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double cv = lds64(cur + r * kRow), cw2 = thr(lds64(cur + r * kRow + kStream)), cw1 = thr(lds64(cur + r * kRow + 2 * kStream));
                     *row_ptr(op, d2i, r) = core.row(a.c, r, rho, mask, cv, cw2, cw1);
                 }
             } else {
 #pragma unroll
+                for (int r = 0; r < R; r++) fetch(s0 + (PD - 1) * R + r);
+                cp_async_commit();
+                cp_async_wait<PD - 1>();
+#pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const double cv = bv[r], cw2 = thr(bw2[r]), cw1 = thr(bw1[r]);
-                    bv[r] = ld2(v2, s0 + R + r);
-                    bw2[r] = ld2(w2, s0 + R + r);
-                    bw1[r] = ld1(s0 + R + r);
+                    const double cv = lds64(cur + r * kRow), cw2 = thr(lds64(cur + r * kRow + kStream)), cw1 = thr(lds64(cur + r * kRow + 2 * kStream));
                     const double o = core.row(a.c, r, rho, mask, cv, cw2, cw1);
                     if (s0 + r >= lag && s0 + r < nout + lag) *row_ptr(op, d2i, r) = o;
                 }
@@ -873,6 +946,7 @@ __global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_synthesis_pair
             core.end_block();
             v2p += step; w2p += step; w1p += step; op += step;
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -949,6 +1023,23 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
 }  // namespace
 
 static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid);
+// dynamic shared memory of the pair kernels' input rings; above 48 KB a kernel needs the opt-in attribute once per device
+constexpr size_t ring_bytes(int depth) { return (size_t)depth * kPR * kCThreads * 8; }
+constexpr size_t kRingBytes = ring_bytes(kPD);
+static int ring_optin(vw_ctx *ctx, const void *func, size_t bytes) {
+    if (bytes <= 48 * 1024) return VW_OK;
+    struct Entry { int device; const void *func; };
+    static std::mutex mu;
+    static std::vector<Entry> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto &e : done)
+        if (e.device == ctx->device && e.func == func) return VW_OK;
+    int rc = vw_cuda_check(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                           "cudaFuncSetAttribute(max dynamic smem, pair kernel)");
+    if (rc) return rc;
+    done.push_back({ctx->device, func});
+    return VW_OK;
+}
 // Levels j and j+1 (d = dilation of level j) in one pass; VW_EUNSUPPORTED when the pair form does not apply (the caller
 // then runs the two levels one by one).
 static bool pair_ok(const vw_ctx *ctx, const VwFilt &f, int l, int64_t d, int mode, ColLat &c) {
@@ -969,12 +1060,13 @@ int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, i
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.mode = mode;
     a.thr = nullptr; a.thr_per_row = 0; a.thr_soft = 0;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat2<15>, kCThreads, 0);
+    static_assert(VW_PAIR_RA == VW_PAIR_R, "kRingBytes assumes one block size");
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat2<15>, kCThreads, kRingBytes);
     dim3 grid;
     // fewer, longer chunks than the single-level kernels: every chunk re-reads 3 (L-1) warm-up rows
     if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
     fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
-    k_column_analysis_lat2<15><<<grid, kCThreads, 0, ctx->stream>>>(a);
+    k_column_analysis_lat2<15><<<grid, kCThreads, kRingBytes, ctx->stream>>>(a);
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice pair) launch");
 }
@@ -998,15 +1090,17 @@ static int launch_pair_synthesis(vw_ctx *ctx, A &a, int64_t n_out, int64_t d, in
     int per_sm = 0;
     dim3 grid;
     if (thr) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, true>, kCThreads, 0);
+        if (int rc = ring_optin(ctx, (const void *)k_column_synthesis_pair<Core, true>, 3 * ring_bytes(Core::DEPTH))) return rc;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, true>, kCThreads, 3 * ring_bytes(Core::DEPTH));
         if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
         fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
-        k_column_synthesis_pair<Core, true><<<grid, kCThreads, 0, ctx->stream>>>(a);
+        k_column_synthesis_pair<Core, true><<<grid, kCThreads, 3 * ring_bytes(Core::DEPTH), ctx->stream>>>(a);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, false>, kCThreads, 0);
+        if (int rc = ring_optin(ctx, (const void *)k_column_synthesis_pair<Core, false>, 3 * ring_bytes(Core::DEPTH))) return rc;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_synthesis_pair<Core, false>, kCThreads, 3 * ring_bytes(Core::DEPTH));
         if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
         fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
-        k_column_synthesis_pair<Core, false><<<grid, kCThreads, 0, ctx->stream>>>(a);
+        k_column_synthesis_pair<Core, false><<<grid, kCThreads, 3 * ring_bytes(Core::DEPTH), ctx->stream>>>(a);
     }
     ctx->launches++;
     return vw_cuda_check(ctx, cudaGetLastError(), "column synthesis (pair) launch");
