@@ -297,3 +297,141 @@ def test_direct_form_pairs_threshold_on_load_equals_the_oracle_denoise(eng):
             dref, tref = cref.swt_denoise(x[i], h, g, levels, mode, wid, -1.0, True)
             assert abs(float(np.asarray(thr)[i]) - tref) <= 1e-12 * tref
             assert float(np.max(np.abs(den[i] - dref))) <= REL * float(np.max(np.abs(x)))
+
+
+# ---- CPU: the lane-pair recurrences of the two-levels-per-pass kernels, lane by lane, against the oracle ----------------
+
+def _pair_analysis_lattice(x, coef):
+    """k_column_analysis_lat2 on the dilation-1 column of a periodic signal: the even lane owns the even rows, the odd
+    lane the odd rows; both walk in step, the neighbouring input row crosses by 'shuffle'.  Returns W_1, W_2, V_2."""
+    k = coef.size - 3
+    t, b = coef[:k - 1], coef[k - 1:]
+    n = x.size
+    n2 = n // 2
+    lead = 48
+    w1, w2, v2 = np.zeros(n), np.zeros(n), np.zeros(n)
+    dl1 = np.zeros((2, k - 1))
+    dl2 = np.zeros((2, k - 1, 2))
+    xprev, vprev = [0.0, 0.0], [0.0, 0.0]
+    for s in range(-lead, n2):
+        xv = [x[(2 * s) % n], x[(2 * s + 1) % n]]
+        send = [xv[0], xprev[1]]                  # the even lane sends its current row, the odd lane its previous one
+        un = [send[1], send[0]]
+        for rho in (0, 1):
+            xprev[rho] = xv[rho]
+            aa = b[0] * xv[rho] + b[1] * un[rho]
+            bb = b[2] * xv[rho] + b[3] * un[rho]
+            for i in range(k - 1):
+                bd = dl1[rho, i]
+                dl1[rho, i] = bb
+                aa, bb = aa + t[i] * bd, bd - t[i] * aa
+            o1 = bb
+            a2 = b[0] * aa + b[1] * vprev[rho]
+            b2 = b[2] * aa + b[3] * vprev[rho]
+            vprev[rho] = aa
+            for i in range(k - 1):
+                bd = dl2[rho, i, s & 1]
+                dl2[rho, i, s & 1] = b2
+                a2, b2 = a2 + t[i] * bd, bd - t[i] * a2
+            if s >= 0:
+                q = 2 * s + rho
+                w1[q], v2[q], w2[q] = o1, a2, b2
+    return w1, w2, v2
+
+
+def _pair_synthesis(v2, w2, w1, row_fn, lag1, lag0):
+    """the skeleton of k_column_synthesis_pair on the dilation-1 column of a periodic signal: both lanes consume own row s of
+    (V_2, W_2) and own row s - lag1 of W_1 in step; row_fn(rho, s, cv, cw2, cw1, exchange) -> output; lags as in the kernel"""
+    n = v2.size
+    n2 = n // 2
+    out = np.zeros(n)
+    steps = n2 + lag1 + lag0 + 2
+    for s in range(steps):
+        cv = [v2[(2 * s + rho) % n] for rho in (0, 1)]
+        cw2 = [w2[(2 * s + rho) % n] for rho in (0, 1)]
+        cw1 = [w1[(2 * (s - lag1) + rho) % n] if s >= lag1 else 0.0 for rho in (0, 1)]
+        res = row_fn(s, cv, cw2, cw1)
+        for rho in (0, 1):
+            o = s - (lag1 + lag0 + rho)
+            if 0 <= o < n2:
+                out[2 * o + rho] = res[rho]
+    return out
+
+
+def _lattice_syn_rows(coef):
+    k = coef.size - 3
+    t, b = coef[:k - 1], coef[k - 1:]
+    dl1 = np.zeros((2, k - 1))
+    dl2 = np.zeros((2, k - 1, 2))
+    y0prev, z0prev = [0.0, 0.0], [0.0, 0.0]
+
+    def row(s, cv, cw2, cw1):
+        z0, z1 = [0.0, 0.0], [0.0, 0.0]
+        for rho in (0, 1):
+            aa, bb = cv[rho], cw2[rho]
+            for i in range(k - 2, -1, -1):
+                an, bb = aa - t[i] * bb, bb + t[i] * aa
+                aa = dl2[rho, i, s & 1]
+                dl2[rho, i, s & 1] = an
+            y0 = b[0] * aa + b[2] * bb
+            y1 = b[1] * aa + b[3] * bb
+            aa = y0prev[rho] + y1
+            y0prev[rho] = y0
+            bb = cw1[rho]
+            for i in range(k - 2, -1, -1):
+                an, bb = aa - t[i] * bb, bb + t[i] * aa
+                aa = dl1[rho, i]
+                dl1[rho, i] = an
+            z0[rho] = b[0] * aa + b[2] * bb
+            z1[rho] = b[1] * aa + b[3] * bb
+        res = [z0[0] + z1[1], z0prev[1] + z1[0]]      # each lane adds the partner's second channel ('shuffle')
+        z0prev[0], z0prev[1] = z0[0], z0[1]
+        return res
+    return row
+
+
+def _direct_syn_rows(h, g):
+    ln = h.size
+    hh = ln // 2
+    acc2 = [dict(), dict()]
+    acc1 = [dict(), dict()]
+    v1prev, w1prev = [0.0, 0.0], [0.0, 0.0]
+
+    def row(s, cv, cw2, cw1):
+        v1 = [0.0, 0.0]
+        for rho in (0, 1):
+            for k in range(ln):
+                acc2[rho][s - k] = acc2[rho].get(s - k, 0.0) + h[k] * cv[rho] + g[k] * cw2[rho]
+            v1[rho] = acc2[rho].pop(s - (ln - 1), 0.0)
+        res = [0.0, 0.0]
+        for rho in (0, 1):
+            ov, ow = (v1prev[1], w1prev[1]) if rho else (v1[0], cw1[0])      # the odd lane applies its own row one step late
+            pv, pw = v1[1 - rho], cw1[1 - rho]
+            for kk in range(hh):
+                j = s - kk
+                acc1[rho][j] = acc1[rho].get(j, 0.0) + h[2 * kk] * ov + g[2 * kk] * ow + h[2 * kk + 1] * pv + g[2 * kk + 1] * pw
+            res[rho] = acc1[rho].pop(s - (hh - 1), 0.0)
+        v1prev[1], w1prev[1] = v1[1], cw1[1]
+        return res
+    return row
+
+
+def test_numpy_lane_pair_recurrences_equal_two_oracle_levels():
+    """What the pair kernels compute, lane by lane with their lags and exchanges, on a periodic signal whose levels 1-2 are the
+    pair (dilation 1): the lattice analysis and synthesis (coif5) and the direct-form synthesis (sym8) against the oracle."""
+    n = 1024
+    x = np.random.default_rng(17).standard_normal(n)
+    t14 = 1e-14 * float(np.max(np.abs(x)))
+    h, g, wid = filters("coif5")
+    coef, _ = _lattice("coif5")
+    wo, vo = cref.decompose(x, h, g, 2, 0)
+    w1, w2, v2 = _pair_analysis_lattice(x, coef)
+    assert max(float(np.max(np.abs(w1 - wo[0]))), float(np.max(np.abs(w2 - wo[1]))), float(np.max(np.abs(v2 - vo)))) <= t14
+    ref = cref.reconstruct(wo, vo, h, g, 0, wid)
+    rec = _pair_synthesis(vo, wo[1], wo[0], _lattice_syn_rows(coef), 29, 14)
+    assert float(np.max(np.abs(rec - ref))) <= t14
+    h, g, wid = filters("sym8")
+    wo, vo = cref.decompose(x, h, g, 2, 0)
+    ref = cref.reconstruct(wo, vo, h, g, 0, wid)
+    rec = _pair_synthesis(vo, wo[1], wo[0], _direct_syn_rows(h * S, g * S), 15, 7)
+    assert float(np.max(np.abs(rec - ref))) <= t14
