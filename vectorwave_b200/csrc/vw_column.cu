@@ -565,7 +565,8 @@ struct ColPairT {
     double *o1; long long ldo1;           // analysis: W_j
     double *o2; long long ldo2;           // analysis: W_{j+1}
     long long n_in, t0, n_out, batch, d;  // d = dilation of level j; a lane walks positions c2 + i * 2d, c2 in [0, 2d)
-    int rows_per_chunk, chunks, mode;     // rows = a lane's own rows (level-(j+1) rows)
+    int rows_per_chunk, chunks, mode;     // chunks of a lane's own rows (level-(j+1) rows); the kernels spread the boundaries evenly
+                                          // themselves and ignore rows_per_chunk
     const double *thr; int thr_per_row, thr_soft;
     P c;                                  // the arithmetic core's coefficients (lattice, or the low-pass taps of a quadrature-mirror pair)
 };
@@ -592,8 +593,9 @@ __device__ __forceinline__ double shfl_partner(unsigned mask, double v) {
 // Input rows of the pair kernels travel through a per-lane ring in shared memory, filled by 8-byte cp.async: ncu showed the
 // pairs read-latency bound (long_scoreboard 1.3-3.2 warps per issue at 8 warps/SM) with a register prefetch of one block (8
 // rows) -- all the ~250 registers allowed.  The ring holds kPD blocks per stream and costs no registers (which is what lets a
-// third CTA onto the SM): rows are requested (kPD-1) blocks before they are used.  Slot [row mod (kPD*R)][thread]: a lane only ever touches its own column of the ring,
-// so neither barriers nor bank conflicts; rows outside the signal (wrap, zero padding) are written with plain stores.
+// third CTA onto the SM): rows are requested (kPD-1) blocks before they are used.  Slot [row mod (kPD*R)][thread]: a lane only
+// ever touches its own column of the ring, so neither barriers nor bank conflicts; rows outside the signal (wrap, zero padding)
+// are written with plain stores.
 #ifndef VW_PAIR_DEPTH
 #define VW_PAIR_DEPTH 2
 #endif
