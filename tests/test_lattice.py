@@ -127,7 +127,7 @@ def eng():
     import vectorwave_b200 as vw
     e = vw.Engine.get()
     yield e
-    for k, v in (("lattice", 7), ("colmin", 0), ("tile", 0), ("fuse", 0)):
+    for k, v in (("lattice", 15), ("colmin", 0), ("tile", 0), ("fuse", 0)):
         e.set_option(k, v)
 
 
@@ -138,7 +138,7 @@ def _both(eng, fn, lattice=3):
     a = fn()
     eng.set_option("lattice", 0)
     b = fn()
-    eng.set_option("lattice", 7)
+    eng.set_option("lattice", 15)
     return a, b
 
 
@@ -202,7 +202,7 @@ def test_pairs_save_launches_and_singles_take_over_where_pairs_do_not_apply(eng)
         l0 = eng.launch_count()
         eng.forward(x, h * S, g * S, 8, mode)
         counts[key] = eng.launch_count() - l0
-    eng.set_option("lattice", 7)
+    eng.set_option("lattice", 15)
     assert counts["singles"] - counts["pairs"] == 3 and counts["symmetric"] == counts["singles"]
 
 
@@ -269,12 +269,21 @@ def test_direct_form_synthesis_pairs_of_16_to_20_tap_filters_against_the_oracle(
         w[:, i, :], v[i] = wo, vo
         refs.append(cref.reconstruct(wo, vo, h, g, mode, wid))
     out = {}
-    for lat in (7, 3):
+    fwd = {}
+    for lat in (15, 3):
         eng.set_option("lattice", lat)
         eng.inverse(w, v, hs, gs, mode, align, order)           # plan cached
         l0 = eng.launch_count()
         out[lat] = (np.asarray(eng.inverse(w, v, hs, gs, mode, align, order)), eng.launch_count() - l0)
-    eng.set_option("lattice", 7)
+        fw, fv = eng.forward(x, hs, gs, levels, mode)
+        fwd[lat] = (np.asarray(fw), np.asarray(fv))
+    eng.set_option("lattice", 15)
+    out[7] = out[15]
+    tx = REL * float(np.max(np.abs(x)))
+    for lat in (15, 3):                                            # the analysis pairs (bit 3) against the oracle too
+        assert float(np.max(np.abs(fwd[lat][0] - w))) <= tx and float(np.max(np.abs(fwd[lat][1] - v))) <= tx
+    if mode == 2:
+        assert np.array_equal(fwd[15][0], fwd[3][0])
     for i in range(b):
         tr = REL * max(float(np.max(np.abs(refs[i]))), float(np.max(np.abs(x))))
         assert float(np.max(np.abs(out[7][0][i] - refs[i]))) <= tr
@@ -336,6 +345,41 @@ def _pair_analysis_lattice(x, coef):
             if s >= 0:
                 q = 2 * s + rho
                 w1[q], v2[q], w2[q] = o1, a2, b2
+    return w1, w2, v2
+
+
+def _pair_analysis_direct(x, h, g):
+    """DirAnaCore of k_column_analysis_pair on the dilation-1 column of a periodic signal: each lane keeps the column around its
+    own rows (own rows + the rows received from the partner) and its own V_1 rows.  Returns W_1, W_2, V_2."""
+    ln = h.size
+    n = x.size
+    n2 = n // 2
+    lead = 24
+    w1, w2, v2 = np.zeros(n), np.zeros(n), np.zeros(n)
+    col = [dict(), dict()]        # per lane: index 2s = own row of step s, 2s-1 = the row received at step s
+    v1 = [dict(), dict()]
+    xprev = [0.0, 0.0]
+    for s in range(-lead, n2):
+        xv = [x[(2 * s) % n], x[(2 * s + 1) % n]]
+        send = [xv[0], xprev[1]]
+        un = [send[1], send[0]]
+        for rho in (0, 1):
+            xprev[rho] = xv[rho]
+            col[rho][2 * s - 1], col[rho][2 * s] = un[rho], xv[rho]
+            ah = ag = 0.0
+            for k in range(ln):
+                c = col[rho].get(2 * s - k, 0.0)
+                ah += h[k] * c
+                ag += g[k] * c
+            v1[rho][s] = ah
+            bh = bg = 0.0
+            for k in range(ln):
+                c = v1[rho].get(s - k, 0.0)
+                bh += h[k] * c
+                bg += g[k] * c
+            if s >= 0:
+                q = 2 * s + rho
+                w1[q], v2[q], w2[q] = ag, bh, bg
     return w1, w2, v2
 
 
@@ -435,3 +479,5 @@ def test_numpy_lane_pair_recurrences_equal_two_oracle_levels():
     ref = cref.reconstruct(wo, vo, h, g, 0, wid)
     rec = _pair_synthesis(vo, wo[1], wo[0], _direct_syn_rows(h * S, g * S), 15, 7)
     assert float(np.max(np.abs(rec - ref))) <= t14
+    w1, w2, v2 = _pair_analysis_direct(x, h * S, g * S)
+    assert max(float(np.max(np.abs(w1 - wo[0]))), float(np.max(np.abs(w2 - wo[1]))), float(np.max(np.abs(v2 - vo)))) <= t14

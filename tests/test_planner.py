@@ -46,8 +46,8 @@ def test_described_plan_is_consistent(l, levels, n):
             elif kind == "column":
                 assert b - a in (0, 1) and halo == (l - 1) * (1 << (a - 1)) * ((1 << (b - a + 1)) - 1)
                 if b > a:
-                    # lattice pairs (30 taps, both directions) or direct-form synthesis pairs (16-20 taps, from level 4)
-                    assert (l == 30 or (l in (16, 18, 20) and not forward and a >= 4)) and 3 * (l - 1) * (1 << (a - 1)) <= n
+                    # lattice pairs (30 taps) or direct-form pairs (16-20 taps: synthesis from level 4, analysis from level 5)
+                    assert (l == 30 or (l in (16, 18, 20) and a >= (5 if forward else 4))) and 3 * (l - 1) * (1 << (a - 1)) <= n
 
 
 def test_forced_tile_and_fuse_are_honoured():

@@ -108,7 +108,7 @@ if __name__ == "__main__":
     ap.add_argument("--l2pf", type=int, default=3)
     ap.add_argument("--lean", type=int, default=3)
     ap.add_argument("--lean_small", type=int, default=1)
-    ap.add_argument("--lattice", type=int, default=7)
+    ap.add_argument("--lattice", type=int, default=15)
     ap.add_argument("--colrpc", type=int, default=0)
     a = ap.parse_args()
     for c in a.configs.split(","):

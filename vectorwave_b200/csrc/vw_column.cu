@@ -613,17 +613,110 @@ __device__ __forceinline__ double lds64(uint32_t src) {
     return v;
 }
 
-#ifndef VW_PAIR_RA
-#define VW_PAIR_RA 8      // own rows per block of the analysis pair (16 measured: config #4 forward 10.15 -> 10.7 ms, the unrolled body doubles)
-#endif
-template <int K>
-__global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat2(const __grid_constant__ ColPair a) {
-    constexpr int L = 2 * K, R = VW_PAIR_RA;
+// Analysis pair: one skeleton (lanes, chunks, ring prefetch, stores), two arithmetic cores -- the lattice (long filters whose
+// table fits one) and the direct form (16-20-tap quadrature-mirror pairs).  A core turns own input row xv (plus what the
+// partner lane holds) into W_j, V_{j+1}, W_{j+1} of that row; LOOKBACK = own rows of history behind an output row.
+struct DirTaps { double h[VW_LEAN_MAX_L]; };     // low-pass taps of a quadrature-mirror pair; g[k] = (-1)^k h[L-1-k]
+
+template <int K> struct LatAnaCore {
+    typedef ColLat Params;
+    static constexpr int L = 2 * K;
     // V_{j+1} at own row i needs V_j at own rows i-(L-1) .. i, each of which needs L-1 level-j rows = L/2 own rows more
-    constexpr int LEAD = ((L - 1 + L / 2 + R - 1) / R) * R;
+    static constexpr int LOOKBACK = L - 1 + L / 2;
+    static constexpr int CTAS = VW_PAIR_CTAS;
+    double dl1[K - 1], dl2[K - 1][2], xprev, vprev;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
+        xprev = vprev = 0.0;
+    }
+    __device__ __forceinline__ void row(const Params &c, int r, int rho, unsigned mask, double xv, double &w1, double &v2, double &w2) {
+        // the neighbouring level-j row: the even lane needs the odd lane's PREVIOUS row, the odd lane the even lane's current one
+        const double un = shfl_partner(mask, rho ? xprev : xv);
+        xprev = xv;
+        double aa = fma(c.b[1], un, c.b[0] * xv);
+        double bb = fma(c.b[3], un, c.b[2] * xv);
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) {
+            const double bd = dl1[k];
+            dl1[k] = bb;
+            const double an = fma(c.t[k], bd, aa);
+            bb = fma(-c.t[k], aa, bd);
+            aa = an;
+        }
+        w1 = bb;
+        double a2 = fma(c.b[1], vprev, c.b[0] * aa);
+        double b2 = fma(c.b[3], vprev, c.b[2] * aa);
+        vprev = aa;
+#pragma unroll
+        for (int k = 0; k < K - 1; k++) {
+            const double bd = dl2[k][r & 1];
+            dl2[k][r & 1] = b2;
+            const double an = fma(c.t[k], bd, a2);
+            b2 = fma(-c.t[k], a2, bd);
+            a2 = an;
+        }
+        v2 = a2; w2 = b2;
+    }
+    __device__ __forceinline__ void end_block() {}
+};
+
+// Direct form.  col[]: the level-j column around the block -- own rows at odd offsets from the block start, the partner's
+// (one level-j row earlier each, received by shuffle) at even ones, so col[L-1 + 2r - k] is u[q - k] for the own row q of step r
+// on either lane; v1[]: the lane's own V_j rows, which are all level j+1 needs (dilation 2 in level-j rows).  Taps ascending, as
+// everywhere (ScalarOps.java:700-723).
+template <int L> struct DirAnaCore {
+    typedef DirTaps Params;
+    static constexpr int R = VW_PAIR_R;
+    static constexpr int LOOKBACK = L - 1 + L / 2;
+#ifndef VW_DIR_CTAS
+#define VW_DIR_CTAS 3
+#endif
+    static constexpr int CTAS = VW_DIR_CTAS;
+    double col[L - 1 + 2 * R], v1[L - 1 + R], xprev;
+    static __device__ __forceinline__ double gk(const Params &c, int k) { return (k & 1) ? -c.h[L - 1 - k] : c.h[L - 1 - k]; }
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < L - 1 + 2 * R; j++) col[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < L - 1 + R; j++) v1[j] = 0.0;
+        xprev = 0.0;
+    }
+    __device__ __forceinline__ void row(const Params &c, int r, int rho, unsigned mask, double xv, double &w1, double &v2, double &w2) {
+        const double un = shfl_partner(mask, rho ? xprev : xv);
+        xprev = xv;
+        col[L - 2 + 2 * r] = un;
+        col[L - 1 + 2 * r] = xv;
+        double ah = 0.0, ag = 0.0;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            ah = fma(c.h[k], col[L - 1 + 2 * r - k], ah);
+            ag = fma(gk(c, k), col[L - 1 + 2 * r - k], ag);
+        }
+        w1 = ag;
+        v1[L - 1 + r] = ah;
+        double bh = 0.0, bg = 0.0;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            bh = fma(c.h[k], v1[L - 1 + r - k], bh);
+            bg = fma(gk(c, k), v1[L - 1 + r - k], bg);
+        }
+        v2 = bh; w2 = bg;
+    }
+    __device__ __forceinline__ void end_block() {
+#pragma unroll
+        for (int j = 0; j < L - 1; j++) col[j] = col[j + 2 * R];
+#pragma unroll
+        for (int j = 0; j < L - 1; j++) v1[j] = v1[j + R];
+    }
+};
+
+template <class Core>
+__global__ void __launch_bounds__(kCThreads, Core::CTAS) k_column_analysis_pair(const __grid_constant__ ColPairT<typename Core::Params> a) {
+    constexpr int R = kPR;
+    constexpr int LEAD = ((Core::LOOKBACK + R - 1) / R) * R;     // warm-up own rows before the chunk: whole blocks
     static_assert(R % 2 == 0 && LEAD % 2 == 0, "delay slots must be compile-time registers");
     const long long gid = (long long)blockIdx.x * kCThreads + threadIdx.x;
-    const int d = (int)a.d;
     const long long d2 = 2 * a.d;
     const long long pid = gid >> 1;            // lane pair = one level-j column of one chunk
     const int rho = (int)(gid & 1);            // this lane's row parity inside the level-j column
@@ -631,7 +724,6 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
     const long long c2 = (pid - chunk * a.d) + (rho ? a.d : 0);   // own level-(j+1) column
     const unsigned mask = __ballot_sync(0xffffffffu, chunk < a.chunks);
     if (chunk >= a.chunks) return;
-    const ColLat &c = a.c;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const long long rows = a.n_out > c2 ? (a.n_out - c2 + d2 - 1) / d2 : 0;   // own rows inside the output range
         // chunk boundaries spread evenly over the longest column (multiples of 8 rows): a short last chunk would keep its warp
@@ -653,10 +745,8 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
         char *w1p = reinterpret_cast<char *>(a.o1 + b * a.ldo1 + (p - a.t0)) - back;
         char *w2p = reinterpret_cast<char *>(a.o2 + b * a.ldo2 + (p - a.t0)) - back;
         const int d2i = (int)d2;
-        double dl1[K - 1], dl2[K - 1][2];
-#pragma unroll
-        for (int k = 0; k < K - 1; k++) { dl1[k] = 0.0; dl2[k][0] = dl2[k][1] = 0.0; }
-        double xprev = 0.0, vprev = 0.0;
+        Core core;
+        core.init();
         const int have = LEAD + left;          // own rows that exist from step 0 on (warm-up + outputs)
         constexpr int RING = kPD * R;          // rows in the ring (a power of two)
         static_assert((RING & (RING - 1)) == 0, "ring slots are taken modulo a power of two");
@@ -675,34 +765,6 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
             fetch(r);
             if ((r + 1) % R == 0) cp_async_commit();
         }
-        auto row = [&](int r, double xv, double &w1, double &v2, double &w2) {
-            // the neighbouring level-j row: the even lane needs the odd lane's PREVIOUS row, the odd lane the even lane's current one
-            const double un = shfl_partner(mask, rho ? xprev : xv);
-            xprev = xv;
-            double aa = fma(c.b[1], un, c.b[0] * xv);
-            double bb = fma(c.b[3], un, c.b[2] * xv);
-#pragma unroll
-            for (int k = 0; k < K - 1; k++) {
-                const double bd = dl1[k];
-                dl1[k] = bb;
-                const double an = fma(c.t[k], bd, aa);
-                bb = fma(-c.t[k], aa, bd);
-                aa = an;
-            }
-            w1 = bb;
-            double a2 = fma(c.b[1], vprev, c.b[0] * aa);
-            double b2 = fma(c.b[3], vprev, c.b[2] * aa);
-            vprev = aa;
-#pragma unroll
-            for (int k = 0; k < K - 1; k++) {
-                const double bd = dl2[k][r & 1];
-                dl2[k][r & 1] = b2;
-                const double an = fma(c.t[k], bd, a2);
-                b2 = fma(-c.t[k], a2, bd);
-                a2 = an;
-            }
-            v2 = a2; w2 = b2;
-        };
         for (int s0 = 0; s0 < steps; s0 += R) {
             // steady state for the whole warp: every lane stores this whole block, and the block requested now -- (kPD-1) blocks
             // ahead -- lies inside the row
@@ -717,7 +779,7 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
                 for (int r = 0; r < R; r++) {
                     const double xv = lds64(cur + r * (kCThreads * 8u));
                     double w1, v2, w2;
-                    row(r, xv, w1, v2, w2);
+                    core.row(a.c, r, rho, mask, xv, w1, v2, w2);
                     *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2;
                 }
             } else {
@@ -729,10 +791,11 @@ __global__ void __launch_bounds__(kCThreads, VW_PAIR_CTAS) k_column_analysis_lat
                 for (int r = 0; r < R; r++) {
                     const double xv = lds64(cur + r * (kCThreads * 8u));
                     double w1, v2, w2;
-                    row(r, xv, w1, v2, w2);
+                    core.row(a.c, r, rho, mask, xv, w1, v2, w2);
                     if (s0 + r >= LEAD && s0 + r < have) { *row_ptr(w1p, d2i, r) = w1; *row_ptr(vp, d2i, r) = v2; *row_ptr(w2p, d2i, r) = w2; }
                 }
             }
+            core.end_block();
             xp += step; vp += step; w1p += step; w2p += step;
         }
         cp_async_wait<0>();
@@ -795,14 +858,10 @@ template <int K> struct LatSynCore {
 // acc1[j]: V_{j-1} at the own output row that completes at in-block step j, fed per step by 8 even taps of the lane's own V_j
 // row and 8 odd taps of the partner's.  The odd lane applies its own row one step late, which makes the accumulator indices
 // the same compile-time constants on both lanes (its outputs then complete one step later than the even lane's: lag + 1).
-struct DirTaps { double h[VW_LEAN_MAX_L]; };
 template <int L> struct DirSynCore {
     typedef DirTaps Params;
     static constexpr int R = VW_PAIR_R, H = L / 2;
     static constexpr int LAG1 = L - 1, LAG0 = H - 1;
-#ifndef VW_DIR_CTAS
-#define VW_DIR_CTAS 3
-#endif
 #ifndef VW_DIR_DEPTH
 #define VW_DIR_DEPTH 2
 #endif
@@ -1024,7 +1083,19 @@ int geometry(const vw_ctx *ctx, int64_t n_out, int64_t d, int64_t batch, int per
 
 }  // namespace
 
-static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid);
+// The pair kernels spread their chunk boundaries evenly themselves (rows_per_chunk is not used), so the chunk count is free:
+// in a batch (one grid row per signal) make the lanes of a signal fill whole CTAs -- 3 chunks x 32 lanes would leave a
+// quarter of every CTA idle (config #3, levels 5-6: rows of 2048 own rows)
+static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid) {
+    if (batch <= 1 || d2 >= kCThreads || (kCThreads % d2) != 0) return;
+    const int64_t q = kCThreads / d2;                              // chunks per CTA
+    const int64_t rows = (n_out + d2 - 1) / d2;
+    int64_t c = ((chunks + q - 1) / q) * q;
+    while (c > q && rows / c < 256) c -= q;                        // keep chunks long against their warm-up rows
+    if (rows / c < 64) return;
+    chunks = (int)c;
+    grid.x = (unsigned)((c * d2 + kCThreads - 1) / kCThreads);
+}
 // dynamic shared memory of the pair kernels' input rings; above 48 KB a kernel needs the opt-in attribute once per device
 constexpr size_t ring_bytes(int depth) { return (size_t)depth * kPR * kCThreads * 8; }
 constexpr size_t kRingBytes = ring_bytes(kPD);
@@ -1052,39 +1123,45 @@ static bool pair_ok(const vw_ctx *ctx, const VwFilt &f, int l, int64_t d, int mo
     return lattice_for(ctx, f32, l, vw_is_qmf(f32.h, f32.g, l), c);
 }
 
-int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, int64_t ldw1, double *w2, int64_t ldw2, double *v2,
-                        int64_t ldv2, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d,
-                        int mode) {
-    ColPair a;
-    if (n_out < 1 || batch < 1 || !pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+template <class Core, class A>
+static int launch_pair_analysis(vw_ctx *ctx, A &a, const double *x, int64_t ldx, double *w1, int64_t ldw1, double *w2, int64_t ldw2,
+                                double *v2, int64_t ldv2, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, int64_t d, int mode) {
     a.x = x; a.ldx = ldx; a.wa = a.wb = nullptr; a.ldwa = a.ldwb = 0;
     a.o0 = v2; a.ldo0 = ldv2; a.o1 = w1; a.ldo1 = ldw1; a.o2 = w2; a.ldo2 = ldw2;
     a.n_in = n_in; a.t0 = t0; a.n_out = n_out; a.batch = batch; a.d = d; a.mode = mode;
     a.thr = nullptr; a.thr_per_row = 0; a.thr_soft = 0;
     int per_sm = 0;
-    static_assert(VW_PAIR_RA == VW_PAIR_R, "kRingBytes assumes one block size");
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_lat2<15>, kCThreads, kRingBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_column_analysis_pair<Core>, kCThreads, kRingBytes);
     dim3 grid;
-    // fewer, longer chunks than the single-level kernels: every chunk re-reads 3 (L-1) warm-up rows
+    // fewer, longer chunks than the single-level kernels: every chunk re-reads its warm-up rows
     if (int rc = geometry(ctx, n_out, 2 * d, batch, per_sm, grid, a.rows_per_chunk, a.chunks, 4 * kPR, 3, 768)) return rc;
     fill_ctas(n_out, 2 * d, batch, a.chunks, grid);
-    k_column_analysis_lat2<15><<<grid, kCThreads, kRingBytes, ctx->stream>>>(a);
+    k_column_analysis_pair<Core><<<grid, kCThreads, kRingBytes, ctx->stream>>>(a);
     ctx->launches++;
-    return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (lattice pair) launch");
+    return vw_cuda_check(ctx, cudaGetLastError(), "column analysis (pair) launch");
 }
 
-// The pair kernels spread their chunk boundaries evenly themselves (rows_per_chunk is not used), so the chunk count is free:
-// in a batch (one grid row per signal) make the lanes of a signal fill whole CTAs -- 3 chunks x 32 lanes would leave a
-// quarter of every CTA idle (config #3, levels 5-6: rows of 2048 own rows)
-static void fill_ctas(int64_t n_out, int64_t d2, int64_t batch, int &chunks, dim3 &grid) {
-    if (batch <= 1 || d2 >= kCThreads || (kCThreads % d2) != 0) return;
-    const int64_t q = kCThreads / d2;                              // chunks per CTA
-    const int64_t rows = (n_out + d2 - 1) / d2;
-    int64_t c = ((chunks + q - 1) / q) * q;
-    while (c > q && rows / c < 256) c -= q;                        // keep chunks long against their warm-up rows
-    if (rows / c < 64) return;
-    chunks = (int)c;
-    grid.x = (unsigned)((c * d2 + kCThreads - 1) / kCThreads);
+static bool dir_pair_ok(const vw_ctx *ctx, const VwFilt &f, int l, int64_t d, int mode, int bit) {
+    return (ctx->opt_lattice & bit) && mode != VW_SYMMETRIC && d >= 1 && d <= (1ll << 28) && (l == 16 || l == 18 || l == 20) &&
+           vw_is_qmf(f.h, f.g, l);
+}
+
+int vw_column_analysis2(vw_ctx *ctx, const double *x, int64_t ldx, double *w1, int64_t ldw1, double *w2, int64_t ldw2, double *v2,
+                        int64_t ldv2, int64_t n_in, int64_t t0, int64_t n_out, int64_t batch, const VwFilt &f, int l, int64_t d,
+                        int mode) {
+    if (n_out < 1 || batch < 1) return VW_EUNSUPPORTED;
+    if (l == 30) {
+        ColPair a;
+        if (!pair_ok(ctx, f, l, d, mode, a.c)) return VW_EUNSUPPORTED;
+        return launch_pair_analysis<LatAnaCore<15>>(ctx, a, x, ldx, w1, ldw1, w2, ldw2, v2, ldv2, n_in, t0, n_out, batch, d, mode);
+    }
+    // 16-20-tap quadrature-mirror pairs: direct form (their decimal tables fit no lattice)
+    if (!dir_pair_ok(ctx, f, l, d, mode, 8)) return VW_EUNSUPPORTED;
+    ColPairT<DirTaps> a;
+    for (int k = 0; k < VW_LEAN_MAX_L; k++) a.c.h[k] = k < l ? f.h[k] : 0.0;
+    if (l == 16) return launch_pair_analysis<DirAnaCore<16>>(ctx, a, x, ldx, w1, ldw1, w2, ldw2, v2, ldv2, n_in, t0, n_out, batch, d, mode);
+    if (l == 18) return launch_pair_analysis<DirAnaCore<18>>(ctx, a, x, ldx, w1, ldw1, w2, ldw2, v2, ldv2, n_in, t0, n_out, batch, d, mode);
+    return launch_pair_analysis<DirAnaCore<20>>(ctx, a, x, ldx, w1, ldw1, w2, ldw2, v2, ldv2, n_in, t0, n_out, batch, d, mode);
 }
 
 template <class Core, class A>
@@ -1129,9 +1206,7 @@ int vw_column_synthesis2(vw_ctx *ctx, const double *v2, int64_t ldv2, const doub
         return launch_pair_synthesis<LatSynCore<15>>(ctx, a, n_out, d, batch, thr_dev != nullptr);
     }
     // 16-20-tap quadrature-mirror pairs: direct form (their decimal tables fit no lattice)
-    if (!(ctx->opt_lattice & 4) || mode == VW_SYMMETRIC || d < 1 || d > (1ll << 28) || (l != 16 && l != 18 && l != 20) ||
-        !vw_is_qmf(f.h, f.g, l))
-        return VW_EUNSUPPORTED;
+    if (!dir_pair_ok(ctx, f, l, d, mode, 4)) return VW_EUNSUPPORTED;
     ColPairT<DirTaps> a;
     for (int k = 0; k < VW_LEAN_MAX_L; k++) a.c.h[k] = k < l ? f.h[k] : 0.0;
     fill_pair_synthesis(a, v2, ldv2, w2, ldw2, w1, ldw1, out, ldo, n_in, t0, n_out, batch, d, mode, thr_dev, thr_per_row, thr_soft);

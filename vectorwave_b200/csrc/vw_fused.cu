@@ -833,9 +833,10 @@ int vw_plan_levels(const vw_ctx *ctx, bool forward, int l, int levels, int64_t n
         if (best[done] == INFINITY) continue;
         // two column levels per pass: the lattice pair kernels (vw_column.cu) exist for 30 taps (both directions); a pair the kernels decline at
         // run time (a table that fits no lattice, SYMMETRIC) is run level by level by the cascade drivers
-        // ... and, for the synthesis of 16-20-tap quadrature-mirror pairs, in direct form from dilation 8 on
-        const bool pair16 = !forward && (l == 16 || l == 18 || l == 20) && (ctx->opt_lattice & 4) &&
-                            done + 1 >= (ctx->opt_colmin > 0 ? (int)ctx->opt_colmin : 4);
+        // ... and, for 16-20-tap quadrature-mirror pairs, in direct form (synthesis from dilation 8 on, analysis from 16 on: the
+        // analysis tile groups of two levels are cheaper than a pair until the halo recompute of levels 7-8 sets in)
+        const bool pair16 = (l == 16 || l == 18 || l == 20) && (ctx->opt_lattice & (forward ? 8 : 4)) &&
+                            done + 1 >= (ctx->opt_colmin > 0 ? (int)ctx->opt_colmin : (forward ? 5 : 4));
         const bool pair_len = ctx->opt_poly != 0 &&
                               ((l == 30 && (ctx->opt_lattice & 2) && done + 1 >= vw_column_min_level(ctx, l, forward)) || pair16);
         for (int nf = 1; nf <= std::max(cap, pair_len ? 2 : 1) && done + nf <= levels; nf++) {

@@ -108,7 +108,7 @@ struct vw_ctx {
     int64_t opt_wave = 1;    // column kernels: size single-signal grids to whole waves
     int64_t opt_colmin = 0;  // first level the column kernels may take (0 = auto: see vw_column_min_level)
     int64_t opt_colrpc = 0;  // developer knob: minimum rows per chunk of the lattice column kernels (0 = built-in)
-    int64_t opt_lattice = 7; // column kernels (vw_column.cu): bit 0 = lattice form for long quadrature-mirror pairs (>= 24 taps) whose taps fit one (vw_lattice.cu), bit 1 = two lattice levels per pass, bit 2 = two direct-form synthesis levels per pass for 16-20-tap pairs
+    int64_t opt_lattice = 15; // column kernels (vw_column.cu): bit 0 = lattice form for long quadrature-mirror pairs (>= 24 taps) whose taps fit one (vw_lattice.cu), bit 1 = two lattice levels per pass, bit 2 / bit 3 = two direct-form synthesis / analysis levels per pass for 16-20-tap pairs
 };
 
 // MutableMultiLevelMODWTResult.applyThresholdToArray (CORE/modwt/MutableMultiLevelMODWTResult.java:97-118):
